@@ -1,0 +1,337 @@
+"""ctypes binding of the C ABI in include/dgcn.h (libdgcn.so, sm_100a kernels).
+
+PyTorch is only the carrier here: it owns device memory (inputs, outputs and the
+scratch workspace handed to the library) and the stream the kernels are put on.
+There is NO CPU or eager fallback: every wrapper raises if the library is not
+built or a tensor is not on a CUDA device.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libdgcn.so")
+
+c_f32p = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+c_i32 = ctypes.c_int32
+
+ACT = {None: 0, "none": 0, "relu": 1, "leakyrelu": 2, "prelu": 3}
+NORM_NONE, NORM_BATCH_EVAL, NORM_BATCH_TRAIN = 0, 1, 2
+CONV = {"edge": 0, "mr": 1}
+AGGR = {"softmax": 0, "softmax_sg": 0, "softmax_sum": 1, "power": 2, "power_sum": 3,
+        "add": 4, "sum": 4, "mean": 5, "max": 6}
+
+
+class BasicConvC(ctypes.Structure):
+    _fields_ = [("weight", c_f32p), ("bias", c_f32p), ("act", c_i32), ("slope", ctypes.c_float),
+                ("prelu_weight", c_f32p), ("norm", c_i32), ("bn_weight", c_f32p), ("bn_bias", c_f32p),
+                ("bn_mean", c_f32p), ("bn_var", c_f32p), ("bn_eps", ctypes.c_float),
+                ("batch_mean_out", c_f32p), ("batch_var_out", c_f32p)]
+
+
+class DilationC(ctypes.Structure):
+    _fields_ = [("k", c_i64), ("dilation", c_i64), ("cols_host", ctypes.POINTER(c_i32))]
+
+
+class GenconvParamsC(ctypes.Structure):
+    _fields_ = [("aggr", c_i32), ("t", ctypes.c_float), ("t_dev", c_f32p), ("p", ctypes.c_float),
+                ("p_dev", c_f32p), ("y", ctypes.c_float), ("y_dev", c_f32p), ("eps", ctypes.c_float),
+                ("msg_norm", c_i32), ("msg_scale", ctypes.c_float), ("msg_scale_dev", c_f32p),
+                ("add_residual", c_i32), ("raw_message", c_i32)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def _declare(lib):
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    lib.dgcn_version.restype = ctypes.c_int
+    lib.dgcn_status_string.restype = ctypes.c_char_p
+    lib.dgcn_status_string.argtypes = [ctypes.c_int]
+    lib.dgcn_last_cuda_error.restype = ctypes.c_char_p
+    lib.dgcn_knn_graph_workspace_bytes.restype = sz
+    lib.dgcn_knn_graph_workspace_bytes.argtypes = [c_i64] * 4
+    lib.dgcn_knn_graph.restype = ctypes.c_int
+    lib.dgcn_knn_graph.argtypes = [vp, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(DilationC), c_i32,
+                                   vp, vp, vp, sz, vp]
+    lib.dgcn_graph_conv_workspace_bytes.restype = sz
+    lib.dgcn_graph_conv_workspace_bytes.argtypes = [c_i32] + [c_i64] * 5
+    lib.dgcn_graph_conv_forward.restype = ctypes.c_int
+    lib.dgcn_graph_conv_forward.argtypes = [c_i32, vp, c_i64, c_i64, c_i64, c_i64, c_i64, vp, vp, c_i64,
+                                            ctypes.POINTER(BasicConvC), c_i64, vp, vp, sz, vp]
+    lib.dgcn_dyn_conv_workspace_bytes.restype = sz
+    lib.dgcn_dyn_conv_workspace_bytes.argtypes = [c_i32] + [c_i64] * 5
+    lib.dgcn_dyn_conv_forward.restype = ctypes.c_int
+    lib.dgcn_dyn_conv_forward.argtypes = [c_i32, vp, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(DilationC),
+                                          ctypes.POINTER(BasicConvC), c_i64, vp, vp, vp, sz, vp]
+    lib.dgcn_graph_conv_backward_workspace_bytes.restype = sz
+    lib.dgcn_graph_conv_backward_workspace_bytes.argtypes = [c_i32] + [c_i64] * 5
+    lib.dgcn_graph_conv_backward.restype = ctypes.c_int
+    lib.dgcn_graph_conv_backward.argtypes = [c_i32, vp, c_i64, c_i64, c_i64, c_i64, c_i64, vp, c_i64,
+                                             ctypes.POINTER(BasicConvC), c_i64, vp, vp, vp, vp, vp, vp, vp,
+                                             vp, sz, vp]
+    lib.dgcn_csr_build_workspace_bytes.restype = sz
+    lib.dgcn_csr_build_workspace_bytes.argtypes = [c_i64, c_i64]
+    lib.dgcn_csr_build.restype = ctypes.c_int
+    lib.dgcn_csr_build.argtypes = [vp, c_i64, c_i64, vp, vp, vp, vp, sz, vp]
+    lib.dgcn_genconv_aggregate.restype = ctypes.c_int
+    lib.dgcn_genconv_aggregate.argtypes = [vp, vp, c_i64, c_i64, vp, vp, vp, vp, ctypes.POINTER(GenconvParamsC),
+                                           vp, vp]
+    lib.dgcn_genconv_aggregate_backward.restype = ctypes.c_int
+    lib.dgcn_genconv_aggregate_backward.argtypes = [vp, vp, c_i64, c_i64, c_i64, vp, vp, vp, vp,
+                                                    ctypes.POINTER(GenconvParamsC), c_i32, vp, vp, vp, vp, vp, vp]
+    lib.dgcn_gather_rows.restype = ctypes.c_int
+    lib.dgcn_gather_rows.argtypes = [vp, c_i64, vp, c_i64, vp, vp]
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        "deep_gcns_torch_b200: %s is missing - build it with "
+                        "`python -m deep_gcns_torch_b200.build` (there is no CPU/eager fallback)" % LIB_PATH)
+                handle = ctypes.CDLL(LIB_PATH)
+                _declare(handle)
+                _lib = handle
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        l = lib()
+        msg = l.dgcn_status_string(rc).decode()
+        extra = l.dgcn_last_cuda_error().decode() if rc == -4 else ""
+        raise RuntimeError("%s failed: %s %s" % (what, msg, extra))
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("deep_gcns_torch_b200 runs on CUDA tensors only (sm_100a kernels, no CPU fallback); "
+                               "got a tensor on %s" % t.device)
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _workspace(nbytes, dev):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+
+
+def _dense_view(x):
+    """(B,C,N,1) or (B,C,N) fp32 with unit point stride -> tensor, B, C, N, stride_b, stride_c."""
+    if x.dim() == 4:
+        if x.size(3) != 1:
+            raise RuntimeError("dense input must be (B, C, N, 1), got %s" % (tuple(x.shape),))
+        x = x.squeeze(-1)
+    if x.dtype != torch.float32:
+        raise RuntimeError("dense path computes in fp32, got %s" % x.dtype)
+    B, C, N = x.shape
+    if N > 1 and x.stride(2) != 1:
+        x = x.contiguous()
+    return x, B, C, N, x.stride(0), x.stride(1)
+
+
+def _dilation(k, dilation, cols):
+    d = DilationC()
+    d.k, d.dilation = int(k), int(dilation)
+    keep = None
+    if cols is not None:
+        arr = (c_i32 * int(k))(*[int(c) for c in cols])
+        d.cols_host = ctypes.cast(arr, ctypes.POINTER(c_i32))
+        keep = arr
+    return d, keep
+
+
+def _f32(t):
+    if t is None:
+        return None
+    t = t.detach()
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return t
+
+
+class ConvParams:
+    """Tensors of one BasicConv([2*C_in, C_out]) (gcn_lib/dense/torch_nn.py:48-58)."""
+
+    def __init__(self, weight, bias=None, act="relu", prelu_weight=None, norm=NORM_NONE, bn_weight=None,
+                 bn_bias=None, bn_mean=None, bn_var=None, bn_eps=1e-5):
+        self.weight = _f32(weight).reshape(weight.shape[0], -1)
+        self.bias = _f32(bias)
+        self.act = ACT[act.lower() if isinstance(act, str) else act]
+        self.prelu_weight = _f32(prelu_weight)
+        self.norm = norm
+        self.bn_weight, self.bn_bias = _f32(bn_weight), _f32(bn_bias)
+        self.bn_mean, self.bn_var = _f32(bn_mean), _f32(bn_var)
+        self.bn_eps = float(bn_eps)
+        self.batch_mean = self.batch_var = None
+
+    def tensors(self):
+        return (self.weight, self.bias, self.prelu_weight, self.bn_weight, self.bn_bias, self.bn_mean, self.bn_var)
+
+    def c_struct(self, dev):
+        c_out = self.weight.shape[0]
+        s = BasicConvC()
+        s.weight, s.bias = _ptr(self.weight), _ptr(self.bias)
+        s.act, s.slope, s.prelu_weight = self.act, 0.2, _ptr(self.prelu_weight)
+        s.norm = self.norm
+        s.bn_weight, s.bn_bias = _ptr(self.bn_weight), _ptr(self.bn_bias)
+        s.bn_mean, s.bn_var, s.bn_eps = _ptr(self.bn_mean), _ptr(self.bn_var), self.bn_eps
+        if self.norm == NORM_BATCH_TRAIN:
+            self.batch_mean = torch.empty(c_out, dtype=torch.float32, device=dev)
+            self.batch_var = torch.empty(c_out, dtype=torch.float32, device=dev)
+            s.batch_mean_out, s.batch_var_out = _ptr(self.batch_mean), _ptr(self.batch_var)
+        return s
+
+
+def knn_graph(x, k, dilation=1, cols=None, exclude_self=False, want_edge_index=True, want_nbr=False):
+    """dgcn_knn_graph: returns (edge_index (2,B,N,k) int64 | None, nbr (B,N,k) int32 | None)."""
+    _require_cuda(x)
+    x3, B, C, N, sb, sc = _dense_view(x)
+    K = int(k) * int(dilation)
+    if K > N - (1 if exclude_self else 0):
+        raise RuntimeError("selected index k out of range")      # what torch.topk says in the reference
+    dev = x3.device
+    with torch.cuda.device(dev):
+        l = lib()
+        dil, keep = _dilation(k, dilation, cols)
+        ei = torch.empty((2, B, N, k), dtype=torch.int64, device=dev) if want_edge_index else None
+        nbr = torch.empty((B, N, k), dtype=torch.int32, device=dev) if want_nbr else None
+        ws = _workspace(l.dgcn_knn_graph_workspace_bytes(B, C, N, K), dev)
+        rc = l.dgcn_knn_graph(_ptr(x3), B, C, N, sb, sc, ctypes.byref(dil), int(bool(exclude_self)), _ptr(ei),
+                              _ptr(nbr), _ptr(ws), ws.numel(), _stream(dev))
+        _check(rc, "dgcn_knn_graph")
+    return ei, nbr
+
+
+def graph_conv_forward(conv, x, prm, edge_index=None, nbr=None):
+    """dgcn_graph_conv_forward: out (B, C_out, N, 1)."""
+    _require_cuda(x, edge_index, nbr, *prm.tensors())
+    x3, B, C, N, sb, sc = _dense_view(x)
+    dev = x3.device
+    c_out = prm.weight.shape[0]
+    if edge_index is not None:
+        if edge_index.dtype != torch.int64:
+            edge_index = edge_index.long()
+        edge_index = edge_index.contiguous()
+        k = edge_index.shape[-1]
+    else:
+        nbr = nbr.contiguous()
+        k = nbr.shape[-1]
+    with torch.cuda.device(dev):
+        l = lib()
+        cs = prm.c_struct(dev)
+        out = torch.empty((B, c_out, N, 1), dtype=torch.float32, device=dev)
+        ws = _workspace(l.dgcn_graph_conv_workspace_bytes(CONV[conv], B, C, c_out, N, k), dev)
+        rc = l.dgcn_graph_conv_forward(CONV[conv], _ptr(x3), B, C, N, sb, sc, _ptr(edge_index), _ptr(nbr), k,
+                                       ctypes.byref(cs), c_out, _ptr(out), _ptr(ws), ws.numel(), _stream(dev))
+        _check(rc, "dgcn_graph_conv_forward")
+    return out
+
+
+def dyn_conv_forward(conv, x, prm, k, dilation=1, cols=None, want_nbr=False):
+    """dgcn_dyn_conv_forward: (out (B, C_out, N, 1), nbr (B,N,k) int32 | None)."""
+    _require_cuda(x, *prm.tensors())
+    x3, B, C, N, sb, sc = _dense_view(x)
+    K = int(k) * int(dilation)
+    if K > N:
+        raise RuntimeError("selected index k out of range")
+    dev = x3.device
+    c_out = prm.weight.shape[0]
+    with torch.cuda.device(dev):
+        l = lib()
+        cs = prm.c_struct(dev)
+        dil, keep = _dilation(k, dilation, cols)
+        out = torch.empty((B, c_out, N, 1), dtype=torch.float32, device=dev)
+        nbr = torch.empty((B, N, k), dtype=torch.int32, device=dev) if want_nbr else None
+        ws = _workspace(l.dgcn_dyn_conv_workspace_bytes(CONV[conv], B, C, c_out, N, K), dev)
+        rc = l.dgcn_dyn_conv_forward(CONV[conv], _ptr(x3), B, C, N, sb, sc, ctypes.byref(dil), ctypes.byref(cs),
+                                     c_out, _ptr(out), _ptr(nbr), _ptr(ws), ws.numel(), _stream(dev))
+        _check(rc, "dgcn_dyn_conv_forward")
+    return out, nbr
+
+
+def csr_build(edge_index, num_nodes):
+    """dgcn_csr_build: (rowptr (N+1), src (E), eid (E)) int32, rows = destinations, stable."""
+    _require_cuda(edge_index)
+    if edge_index.dtype != torch.int64:
+        edge_index = edge_index.long()
+    edge_index = edge_index.contiguous()
+    E = edge_index.shape[1]
+    dev = edge_index.device
+    with torch.cuda.device(dev):
+        l = lib()
+        rowptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=dev)
+        src = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        eid = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        ws = _workspace(l.dgcn_csr_build_workspace_bytes(num_nodes, E), dev)
+        rc = l.dgcn_csr_build(_ptr(edge_index), E, num_nodes, _ptr(rowptr), _ptr(src), _ptr(eid), _ptr(ws),
+                              ws.numel(), _stream(dev))
+        _check(rc, "dgcn_csr_build")
+    return rowptr, src[:E], eid[:E]
+
+
+def _scalar(prm, name, value):
+    """python float -> host field; tensor (nn.Parameter) -> device pointer (no host sync)."""
+    if torch.is_tensor(value):
+        v = _f32(value)
+        setattr(prm, name + "_dev", _ptr(v))
+        setattr(prm, name, 0.0)
+        return v
+    setattr(prm, name, float(value))
+    setattr(prm, name + "_dev", None)
+    return None
+
+
+def genconv_params(aggr, t=1.0, p=1.0, y=0.0, eps=1e-7, msg_scale=None, add_residual=True):
+    if aggr not in AGGR:
+        raise NotImplementedError("To be implemented")           # torch_message.py:84-85
+    prm = GenconvParamsC()
+    prm.aggr = AGGR[aggr]
+    keep = [_scalar(prm, "t", t), _scalar(prm, "p", p), _scalar(prm, "y", y)]
+    prm.eps = float(eps)
+    prm.msg_norm = 0 if msg_scale is None else 1
+    keep.append(_scalar(prm, "msg_scale", 1.0 if msg_scale is None else msg_scale))
+    prm.add_residual = int(bool(add_residual))
+    prm.raw_message = 0
+    return prm, keep
+
+
+def genconv_aggregate(x_src, x_dst, csr, prm, edge_attr=None):
+    """dgcn_genconv_aggregate: out (N, C) = x_dst + MsgNorm(aggregate(message))."""
+    rowptr, src, eid = csr
+    _require_cuda(x_src, x_dst, rowptr, src, eid, edge_attr)
+    x_src, x_dst, edge_attr = _f32(x_src), _f32(x_dst), _f32(edge_attr)
+    N, C = rowptr.numel() - 1, x_src.shape[1]
+    dev = x_src.device
+    with torch.cuda.device(dev):
+        out = torch.empty((N, C), dtype=torch.float32, device=dev)
+        rc = lib().dgcn_genconv_aggregate(_ptr(x_src), _ptr(x_dst), N, C, _ptr(rowptr), _ptr(src), _ptr(eid),
+                                          _ptr(edge_attr), ctypes.byref(prm), _ptr(out), _stream(dev))
+        _check(rc, "dgcn_genconv_aggregate")
+    return out
+
+
+def gather_rows(x, rows):
+    _require_cuda(x, rows)
+    x = _f32(x)
+    rows = rows.to(torch.int32).contiguous()
+    R, C = rows.numel(), x.shape[1]
+    with torch.cuda.device(x.device):
+        out = torch.empty((R, C), dtype=torch.float32, device=x.device)
+        _check(lib().dgcn_gather_rows(_ptr(x), C, _ptr(rows), R, _ptr(out), _stream(x.device)), "dgcn_gather_rows")
+    return out

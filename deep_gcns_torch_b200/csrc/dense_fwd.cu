@@ -1,0 +1,586 @@
+// Dense path, forward: C ABI entry points dgcn_knn_graph / dgcn_graph_conv_forward /
+// dgcn_dyn_conv_forward and the node-level kernels around the selection kernels.
+#include "knn.cuh"
+
+namespace dgcn {
+
+// ---- launch helpers for the selection kernels -------------------------------------
+static size_t knn_slab_clouds(int64_t B, int64_t N) {
+  const int64_t ldd = (N + 3) / 4 * 4;
+  const int64_t per_cloud = N * ldd * 4;
+  int64_t nb = (96ll << 20) / (per_cloud > 0 ? per_cloud : 1);
+  if (nb < 1) nb = 1;
+  if (nb > B) nb = B;
+  return static_cast<size_t>(nb);
+}
+
+size_t knn_workspace_bytes(int64_t B, int64_t C, int64_t N, int64_t K) {
+  size_t bytes = align_up(static_cast<size_t>(B) * N * 4, 256);
+  if (K > SMALL_K_MAX) {
+    const int64_t ldd = (N + 3) / 4 * 4;
+    bytes += align_up(knn_slab_clouds(B, N) * N * ldd * 4, 256);
+  }
+  return bytes + 256;
+}
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Runs the selection (+ fused consumer described by a.epi) on `stream`.
+int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream) {
+  const int B = a.B, N = a.N, K = a.K;
+  float* sq = ws.take<float>(static_cast<size_t>(B) * N);
+  if (!ws.ok) return DGCN_ERR_WORKSPACE;
+  a.sq = sq;
+  sqnorm_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(a.x, a.sb, a.sc, a.C, N, sq);
+  DGCN_LAUNCH_CHECK();
+  const dim3 grid(ceil_div(N, TILE), B);
+  if (K <= 32) {
+    const size_t smem = sizeof(SmallSmem<1>);
+    DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    knn_small_kernel<1><<<grid, NTHREADS, smem, stream>>>(a);
+    DGCN_LAUNCH_CHECK();
+    return DGCN_OK;
+  }
+  if (K <= SMALL_K_MAX) {
+    const size_t smem = sizeof(SmallSmem<2>);
+    DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    knn_small_kernel<2><<<grid, NTHREADS, smem, stream>>>(a);
+    DGCN_LAUNCH_CHECK();
+    return DGCN_OK;
+  }
+  if (K > LARGE_K_MAX) return DGCN_ERR_UNSUPPORTED;
+  const int ldd = (N + 3) / 4 * 4;
+  const int nbmax = static_cast<int>(knn_slab_clouds(B, N));
+  float* drows = ws.take<float>(static_cast<size_t>(nbmax) * N * ldd);
+  if (!ws.ok) return DGCN_ERR_WORKSPACE;
+  const int KP = next_pow2(K);
+  const size_t per_warp = static_cast<size_t>(KP) * 8 + static_cast<size_t>(N) * 4 + MAX_KEEP * 4;
+  int warps = static_cast<int>((200u << 10) / per_warp);
+  if (warps < 1) return DGCN_ERR_UNSUPPORTED;   // a single row does not fit in shared memory
+  if (warps > 4) warps = 4;
+  const size_t smem = per_warp * warps;
+  DGCN_CUDA_TRY(cudaFuncSetAttribute(select_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+  for (int b0 = 0; b0 < B; b0 += nbmax) {
+    const int nb = (B - b0 < nbmax) ? (B - b0) : nbmax;
+    dist_rows_kernel<<<dim3(ceil_div(N, TILE), ceil_div(N, TILE), nb), NTHREADS, 0, stream>>>(a, b0, drows, ldd);
+    DGCN_LAUNCH_CHECK();
+    const int64_t rows = static_cast<int64_t>(nb) * N;
+    select_rows_kernel<<<static_cast<unsigned>(ceil_div(rows, warps)), warps * 32, smem, stream>>>(
+        a, b0, nb, drows, ldd, KP, N, warps);
+    DGCN_LAUNCH_CHECK();
+  }
+  return DGCN_OK;
+}
+
+int fill_knn_args(KnnArgs& a, const float* x, int64_t B, int64_t C, int64_t N, int64_t stride_b,
+                  int64_t stride_c, const dgcn_dilation* dil, int exclude_self) {
+  if (!x || !dil || B <= 0 || C <= 0 || N <= 0 || dil->k <= 0 || dil->dilation <= 0) return DGCN_ERR_BAD_ARG;
+  if (B > 65535 || N > (1 << 30) || C > (1 << 20)) return DGCN_ERR_UNSUPPORTED;
+  const int64_t K = dil->k * dil->dilation;
+  if (K > N - (exclude_self ? 1 : 0)) return DGCN_ERR_BAD_ARG;   // torch.topk: k out of range
+  if (dil->k > MAX_KEEP) return DGCN_ERR_UNSUPPORTED;
+  a.x = x; a.sb = stride_b; a.sc = stride_c;
+  a.B = static_cast<int>(B); a.C = static_cast<int>(C); a.N = static_cast<int>(N);
+  a.vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && stride_b % 4 == 0 && stride_c % 4 == 0 && N % 4 == 0) ? 1 : 0;
+  a.sq = nullptr;
+  a.K = static_cast<int>(K); a.k = static_cast<int>(dil->k); a.dilation = static_cast<int>(dil->dilation);
+  a.exclude_self = exclude_self ? 1 : 0;
+  a.has_cols = dil->cols_host ? 1 : 0;
+  for (int l = 0; l < MAX_KEEP; ++l) a.cols[l] = 0;
+  if (dil->cols_host) {
+    for (int l = 0; l < a.k; ++l) {
+      int c = dil->cols_host[l];
+      if (c < 0 || c >= K) return DGCN_ERR_BAD_ARG;
+      a.cols[l] = c;
+    }
+  }
+  a.epi = Epilogue{};
+  a.epi.mode = EPI_INDEX;
+  return DGCN_OK;
+}
+
+// ---- node-level kernels ---------------------------------------------------------------
+// EdgeConv weight split: W.[x_i ; x_j - x_i] = (W1 - W2) x_i + W2 x_j.
+// wk[c][m] (k-major, m < 2*co): m < co -> W1[m][c] - W2[m][c]; else W2[m-co][c].  bk = (bias | 0).
+__global__ void pack_edge_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                         int ci, int co, float* __restrict__ wk, float* __restrict__ bk) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ci * 2 * co) {
+    int c = i / (2 * co), m = i % (2 * co);
+    float v;
+    if (m < co) v = w[m * 2 * ci + c] - w[m * 2 * ci + ci + c];
+    else v = w[(m - co) * 2 * ci + ci + c];
+    wk[i] = v;
+  }
+  if (i < 2 * co) bk[i] = (i < co && bias) ? bias[i] : 0.f;
+}
+// MRConv weight transpose: wk[kk][m] = W[m][kk], kk < 2*ci
+__global__ void pack_mr_weights_kernel(const float* __restrict__ w, int ci2, int co, float* __restrict__ wk) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ci2 * co) {
+    int kk = i / co, m = i % co;
+    wk[i] = w[m * ci2 + kk];
+  }
+}
+
+// (B,C,N) strided -> (B,N,C) contiguous
+__global__ void to_node_major_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C, int N,
+                                     float* __restrict__ xt) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int c = c0 + r, n = n0 + threadIdx.x;
+    t[r][threadIdx.x] = (c < C && n < N) ? __ldg(x + b * sb + c * sc + n) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int n = n0 + r, c = c0 + threadIdx.x;
+    if (n < N && c < C) xt[(static_cast<int64_t>(b) * N + n) * C + c] = t[threadIdx.x][r];
+  }
+}
+
+// PQ[b][n][m] = sum_c X[b][c][n] * wk[c][m] + bk[m]      (rows = points, cols = m)
+__global__ void __launch_bounds__(NTHREADS, 2)
+    node_pq_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C, int N, int vec,
+                   const float* __restrict__ wk, const float* __restrict__ bk, int M,
+                   float* __restrict__ pq) {
+  __shared__ TileSmem ts;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int b = blockIdx.z, n0 = blockIdx.y * TILE, m0 = blockIdx.x * TILE;
+  KMajor A = kmajor1(x + b * sb, sc, C, N, vec != 0);
+  KMajor Bm = kmajor1(wk, M, C, M, (M % 4) == 0);
+  float acc[8][8];
+  tile_product(ts, A, n0, Bm, m0, acc);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + tile_row(ty, i);
+    if (n >= N) continue;
+    float* row = pq + (static_cast<int64_t>(b) * N + n) * M;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int m = m0 + tile_col(tx, j);
+      if (m < M) row[m] = acc[i][j] + __ldg(bk + m);
+    }
+  }
+}
+
+// MRConv node update: out[b][m][n] = norm(act(sum_kk wk[kk][m] * [x ; r][kk][n] + bias[m]))
+// rows = m, cols = points.  Train mode stores act() and per-CTA partial statistics.
+struct MrNodeArgs {
+  const float* x; int64_t sb, sc; const float* r; int ci, N, vec;
+  const float* wk; const float* bias; int co;
+  float slope; const float* prelu;
+  int norm; const float* bn_w; const float* bn_b; const float* bn_m; const float* bn_v; float bn_eps;
+  float* out; float* partial;
+};
+__global__ void __launch_bounds__(NTHREADS, 2) mr_node_kernel(const MrNodeArgs g) {
+  __shared__ TileSmem ts;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int b = blockIdx.z, m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
+  KMajor A = kmajor1(g.wk, g.co, 2 * g.ci, g.co, (g.co % 4) == 0);
+  KMajor Bm = kmajor2(g.x + b * g.sb, g.sc, g.ci, g.r + static_cast<int64_t>(b) * g.ci * g.N, g.N, 2 * g.ci,
+                      g.N, g.vec != 0);
+  float acc[8][8];
+  tile_product(ts, A, m0, Bm, n0, acc);
+  const float slope = g.prelu ? __ldg(g.prelu) : g.slope;
+  const bool train = g.norm == DGCN_NORM_BATCH_TRAIN;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + tile_row(ty, i);
+    float s = 1.f, t = 0.f, bias = 0.f;
+    if (m < g.co) {
+      bias = g.bias ? __ldg(g.bias + m) : 0.f;
+      if (g.norm == DGCN_NORM_BATCH_EVAL) {
+        float inv = 1.0f / sqrtf(__ldg(g.bn_v + m) + g.bn_eps);
+        s = (g.bn_w ? __ldg(g.bn_w + m) : 1.f) * inv;
+        t = (g.bn_b ? __ldg(g.bn_b + m) : 0.f) - __ldg(g.bn_m + m) * s;
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + tile_col(tx, j);
+      float a = act_apply(acc[i][j] + bias, slope);
+      if (m < g.co && n < g.N) {
+        g.out[(static_cast<int64_t>(b) * g.co + m) * g.N + n] = fmaf(s, a, t);
+        s1 += a;
+        s2 += a * a;
+      }
+    }
+    if (train) {   // reduce over the 16 tx lanes that share this row (lanes differ in low 4 bits)
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (tx == 0 && m < g.co) {
+        const int64_t slot = static_cast<int64_t>(b) * gridDim.x + blockIdx.x;
+        g.partial[(slot * 2 + 0) * g.co + m] = s1;
+        g.partial[(slot * 2 + 1) * g.co + m] = s2;
+      }
+    }
+  }
+}
+
+// Batch statistics from partial sums (fixed order, fp64) -> (scale, shift) and the
+// batch mean / biased variance the host needs for the running-stat update
+// (torch BatchNorm2d training semantics: normalise with biased variance).
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int64_t np, int C, double count,
+                                   const float* __restrict__ bn_w, const float* __restrict__ bn_b, float eps,
+                                   float* __restrict__ st, float* __restrict__ mean_out,
+                                   float* __restrict__ var_out) {
+  __shared__ double r1[256], r2[256];
+  const int c = blockIdx.x;
+  double a1 = 0.0, a2 = 0.0;
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) {
+    a1 += static_cast<double>(partial[(i * 2 + 0) * C + c]);
+    a2 += static_cast<double>(partial[(i * 2 + 1) * C + c]);
+  }
+  r1[threadIdx.x] = a1;
+  r2[threadIdx.x] = a2;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      r1[threadIdx.x] += r1[threadIdx.x + o];
+      r2[threadIdx.x] += r2[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double mean = r1[0] / count;
+    double var = r2[0] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float inv = 1.0f / sqrtf(static_cast<float>(var) + eps);
+    float s = (bn_w ? bn_w[c] : 1.f) * inv;
+    st[c] = s;
+    st[C + c] = (bn_b ? bn_b[c] : 0.f) - static_cast<float>(mean) * s;
+    if (mean_out) mean_out[c] = static_cast<float>(mean);
+    if (var_out) var_out[c] = static_cast<float>(var);
+  }
+}
+// out = s >= 0 ? s*out + t : s*out_min + t   (out_min may be null: plain affine)
+__global__ void bn_apply_kernel(float* __restrict__ out, const float* __restrict__ out_min,
+                                const float* __restrict__ st, int C, int N, int64_t total) {
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = static_cast<int>((i / N) % C);
+  float s = st[c], t = st[C + c];
+  float v = (s >= 0.f || out_min == nullptr) ? out[i] : out_min[i];
+  out[i] = fmaf(s, v, t);
+}
+
+// ---- static graph: gather / max over a given edge list -----------------------------
+struct GatherArgs {
+  Epilogue e;
+  const int64_t* edge_index;   // (2,B,N,k) or null
+  const int32_t* nbr;          // (B,N,k)   or null
+  int B, N, k;
+};
+__global__ void __launch_bounds__(256) graph_gather_kernel(const GatherArgs g) {
+  __shared__ float smax[32][33];
+  __shared__ float smin[32][33];
+  __shared__ float red[8][2][32];
+  const Epilogue& e = g.e;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, i0 = blockIdx.x * 32;
+  const int N = g.N, k = g.k;
+  const int64_t node0 = static_cast<int64_t>(b) * N;
+  const bool edge = e.mode == EPI_EDGE;
+  const bool train = edge && e.norm == DGCN_NORM_BATCH_TRAIN;
+  const int nch = edge ? e.c_out : e.c_in;
+  const float slope = edge ? epi_slope(e) : 0.f;
+  const int64_t plane = static_cast<int64_t>(g.B) * N * k;
+  for (int c0 = 0; c0 < nch; c0 += 32) {
+    const int c = c0 + lane;
+    float s1 = 0.f, s2 = 0.f, bs = 1.f, bt = 0.f;
+    if (edge) bn_affine(e, c, bs, bt);
+    for (int u = 0; u < 4; ++u) {
+      const int il = warp * 4 + u, i = i0 + il;
+      if (i >= N) continue;
+      float vmax = -INFINITY, vmin = INFINITY;
+      if (c < nch) {
+        for (int l = 0; l < k; ++l) {
+          const int64_t o = (node0 + i) * k + l;
+          int64_t j, ic;
+          if (g.edge_index) {
+            j = g.edge_index[o];
+            ic = g.edge_index[plane + o];
+          } else {
+            j = g.nbr[o];
+            ic = i;
+          }
+          j = j < 0 ? 0 : (j >= N ? N - 1 : j);
+          ic = ic < 0 ? 0 : (ic >= N ? N - 1 : ic);
+          float a;
+          if (edge) {
+            const int ld = 2 * e.c_out;
+            a = act_apply(__ldg(e.pq + (node0 + ic) * ld + c) + __ldg(e.pq + (node0 + j) * ld + e.c_out + c), slope);
+            s1 += a;
+            s2 += a * a;
+          } else {
+            a = __ldg(e.xt + (node0 + j) * e.c_in + c) - __ldg(e.xt + (node0 + ic) * e.c_in + c);
+          }
+          vmax = fmaxf(vmax, a);
+          vmin = fminf(vmin, a);
+        }
+      }
+      if (train || !edge) {
+        smax[lane][il] = vmax;
+        smin[lane][il] = vmin;
+      } else {
+        smax[lane][il] = bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt);
+      }
+    }
+    if (train) {
+      red[warp][0][lane] = s1;
+      red[warp][1][lane] = s2;
+    }
+    __syncthreads();
+    float* dst = edge ? e.out : e.r_out;
+    for (int t = tid; t < 32 * 32; t += 256) {
+      const int cc = t >> 5, il = t & 31;
+      if (c0 + cc < nch && i0 + il < N) {
+        int64_t o = (static_cast<int64_t>(b) * nch + c0 + cc) * N + i0 + il;
+        dst[o] = smax[cc][il];
+        if (train) e.out_min[o] = smin[cc][il];
+      }
+    }
+    if (train && tid < 64) {
+      const int which = tid >> 5, cc = tid & 31;
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += red[w][which][cc];
+      const int64_t cta = static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x;
+      if (c0 + cc < nch) e.partial[(cta * 2 + which) * nch + c0 + cc] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- planning -----------------------------------------------------------------------------
+struct ConvPlan {
+  size_t wk, bk, pq, xt, r, out_min, partial, st;   // element counts (floats)
+  int64_t n_partial;
+};
+static ConvPlan conv_plan(int conv, int64_t B, int64_t ci, int64_t co, int64_t N, int64_t K, bool fused) {
+  ConvPlan p{};
+  p.st = 2 * co;
+  if (conv == DGCN_CONV_EDGE) {
+    p.wk = ci * 2 * co;
+    p.bk = 2 * co;
+    p.pq = B * N * 2 * co;
+    p.out_min = B * co * N;
+    int64_t tiles = fused ? (K <= SMALL_K_MAX ? ceil_div(N, TILE) * B : B * N) : ceil_div(N, 32) * B;
+    p.n_partial = tiles;
+    p.partial = tiles * 2 * co;
+  } else {
+    p.wk = 2 * ci * co;
+    p.xt = B * N * ci;
+    p.r = B * ci * N;
+    p.n_partial = B * ceil_div(N, TILE);
+    p.partial = p.n_partial * 2 * co;
+  }
+  return p;
+}
+static size_t conv_plan_bytes(const ConvPlan& p) {
+  size_t b = 0;
+  for (size_t v : {p.wk, p.bk, p.pq, p.xt, p.r, p.out_min, p.partial, p.st}) b += align_up(v * 4, 256);
+  return b + 256;
+}
+
+static int check_conv_args(int conv, const float* x, int64_t B, int64_t ci, int64_t N, const dgcn_basic_conv* p,
+                           int64_t co, const float* out) {
+  if (conv != DGCN_CONV_EDGE && conv != DGCN_CONV_MR) return DGCN_ERR_UNSUPPORTED;
+  if (!x || !p || !p->weight || !out || B <= 0 || ci <= 0 || co <= 0 || N <= 0) return DGCN_ERR_BAD_ARG;
+  if (p->act < DGCN_ACT_NONE || p->act > DGCN_ACT_PRELU) return DGCN_ERR_UNSUPPORTED;
+  if (p->act == DGCN_ACT_PRELU && !p->prelu_weight) return DGCN_ERR_BAD_ARG;
+  if (p->norm < DGCN_NORM_NONE || p->norm > DGCN_NORM_BATCH_TRAIN) return DGCN_ERR_UNSUPPORTED;
+  if (p->norm == DGCN_NORM_BATCH_EVAL && (!p->bn_mean || !p->bn_var)) return DGCN_ERR_BAD_ARG;
+  if (B > 65535) return DGCN_ERR_UNSUPPORTED;
+  return DGCN_OK;
+}
+
+float act_slope_of(const dgcn_basic_conv* p) {
+  switch (p->act) {
+    case DGCN_ACT_RELU: return 0.f;
+    case DGCN_ACT_LEAKYRELU: return p->slope;
+    case DGCN_ACT_PRELU: return 0.f;   // read from prelu_weight on device
+    default: return 1.f;
+  }
+}
+
+// Shared body of graph_conv_forward (graph given) and dyn_conv_forward (graph fused).
+static int conv_forward(int conv, const float* x, int64_t B, int64_t ci, int64_t N, int64_t sb, int64_t sc,
+                        const int64_t* edge_index, const int32_t* nbr, int64_t k, const dgcn_dilation* dil,
+                        const dgcn_basic_conv* p, int64_t co, float* out, int32_t* nbr_out, Workspace& ws,
+                        cudaStream_t stream) {
+  const bool fused = dil != nullptr;
+  const int64_t K = fused ? dil->k * dil->dilation : k;
+  const int64_t keep = fused ? dil->k : k;
+  ConvPlan pl = conv_plan(conv, B, ci, co, N, K, fused);
+  const bool train = p->norm == DGCN_NORM_BATCH_TRAIN;
+  const int vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && sb % 4 == 0 && sc % 4 == 0 && N % 4 == 0) ? 1 : 0;
+
+  Epilogue e{};
+  e.nbr = nbr_out;
+  e.slope = act_slope_of(p);
+  e.prelu = p->act == DGCN_ACT_PRELU ? p->prelu_weight : nullptr;
+  e.norm = p->norm;
+  e.bn_w = p->bn_weight; e.bn_b = p->bn_bias; e.bn_m = p->bn_mean; e.bn_v = p->bn_var; e.bn_eps = p->bn_eps;
+  e.c_out = static_cast<int>(co);
+  e.c_in = static_cast<int>(ci);
+  float* wk = ws.take<float>(pl.wk);
+  float* st = ws.take<float>(pl.st);
+  float* partial = train ? ws.take<float>(pl.partial) : nullptr;
+  if (!ws.ok) return DGCN_ERR_WORKSPACE;
+
+  if (conv == DGCN_CONV_EDGE) {
+    float* bk = ws.take<float>(pl.bk);
+    float* pq = ws.take<float>(pl.pq);
+    float* out_min = train ? ws.take<float>(pl.out_min) : nullptr;
+    if (!ws.ok) return DGCN_ERR_WORKSPACE;
+    const int M = static_cast<int>(2 * co);
+    pack_edge_weights_kernel<<<static_cast<unsigned>(ceil_div(ci * M > M ? ci * M : M, 256)), 256, 0, stream>>>(
+        p->weight, p->bias, static_cast<int>(ci), static_cast<int>(co), wk, bk);
+    DGCN_LAUNCH_CHECK();
+    node_pq_kernel<<<dim3(ceil_div(M, TILE), ceil_div(N, TILE), B), NTHREADS, 0, stream>>>(
+        x, sb, sc, static_cast<int>(ci), static_cast<int>(N), vec, wk, bk, M, pq);
+    DGCN_LAUNCH_CHECK();
+    e.mode = EPI_EDGE;
+    e.pq = pq;
+    e.out = out;
+    e.out_min = out_min;
+    e.partial = partial;
+    if (fused) {
+      KnnArgs a;
+      int rc = fill_knn_args(a, x, B, ci, N, sb, sc, dil, 0);
+      if (rc != DGCN_OK) return rc;
+      a.epi = e;
+      rc = launch_knn(a, ws, stream);
+      if (rc != DGCN_OK) return rc;
+    } else {
+      GatherArgs g{e, edge_index, nbr, static_cast<int>(B), static_cast<int>(N), static_cast<int>(k)};
+      graph_gather_kernel<<<dim3(ceil_div(N, 32), B), 256, 0, stream>>>(g);
+      DGCN_LAUNCH_CHECK();
+    }
+    if (train) {
+      bn_finalize_kernel<<<static_cast<unsigned>(co), 256, 0, stream>>>(
+          partial, pl.n_partial, static_cast<int>(co), static_cast<double>(B) * N * keep, p->bn_weight, p->bn_bias,
+          p->bn_eps, st, p->batch_mean_out, p->batch_var_out);
+      DGCN_LAUNCH_CHECK();
+      const int64_t total = B * co * N;
+      bn_apply_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, stream>>>(
+          out, out_min, st, static_cast<int>(co), static_cast<int>(N), total);
+      DGCN_LAUNCH_CHECK();
+    }
+    return DGCN_OK;
+  }
+
+  // MRConv: r = max_j x_j - x_i (gather on a node-major copy), then the node update GEMM
+  float* xt = ws.take<float>(pl.xt);
+  float* r = ws.take<float>(pl.r);
+  if (!ws.ok) return DGCN_ERR_WORKSPACE;
+  pack_mr_weights_kernel<<<static_cast<unsigned>(ceil_div(2 * ci * co, 256)), 256, 0, stream>>>(
+      p->weight, static_cast<int>(2 * ci), static_cast<int>(co), wk);
+  DGCN_LAUNCH_CHECK();
+  to_node_major_kernel<<<dim3(ceil_div(N, 32), ceil_div(ci, 32), B), dim3(32, 8), 0, stream>>>(
+      x, sb, sc, static_cast<int>(ci), static_cast<int>(N), xt);
+  DGCN_LAUNCH_CHECK();
+  e.mode = EPI_MR;
+  e.xt = xt;
+  e.r_out = r;
+  if (fused) {
+    KnnArgs a;
+    int rc = fill_knn_args(a, x, B, ci, N, sb, sc, dil, 0);
+    if (rc != DGCN_OK) return rc;
+    a.epi = e;
+    rc = launch_knn(a, ws, stream);
+    if (rc != DGCN_OK) return rc;
+  } else {
+    GatherArgs g{e, edge_index, nbr, static_cast<int>(B), static_cast<int>(N), static_cast<int>(k)};
+    graph_gather_kernel<<<dim3(ceil_div(N, 32), B), 256, 0, stream>>>(g);
+    DGCN_LAUNCH_CHECK();
+  }
+  MrNodeArgs m{};
+  m.x = x; m.sb = sb; m.sc = sc; m.r = r; m.ci = static_cast<int>(ci); m.N = static_cast<int>(N); m.vec = vec;
+  m.wk = wk; m.bias = p->bias; m.co = static_cast<int>(co);
+  m.slope = e.slope; m.prelu = e.prelu;
+  m.norm = p->norm; m.bn_w = p->bn_weight; m.bn_b = p->bn_bias; m.bn_m = p->bn_mean; m.bn_v = p->bn_var;
+  m.bn_eps = p->bn_eps;
+  m.out = out; m.partial = partial;
+  mr_node_kernel<<<dim3(ceil_div(N, TILE), ceil_div(co, TILE), B), NTHREADS, 0, stream>>>(m);
+  DGCN_LAUNCH_CHECK();
+  if (train) {
+    bn_finalize_kernel<<<static_cast<unsigned>(co), 256, 0, stream>>>(
+        partial, pl.n_partial, static_cast<int>(co), static_cast<double>(B) * N, p->bn_weight, p->bn_bias, p->bn_eps,
+        st, p->batch_mean_out, p->batch_var_out);
+    DGCN_LAUNCH_CHECK();
+    const int64_t total = B * co * N;
+    bn_apply_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, stream>>>(
+        out, nullptr, st, static_cast<int>(co), static_cast<int>(N), total);
+    DGCN_LAUNCH_CHECK();
+  }
+  return DGCN_OK;
+}
+
+}  // namespace dgcn
+
+using namespace dgcn;
+
+extern "C" {
+
+size_t dgcn_knn_graph_workspace_bytes(int64_t B, int64_t C, int64_t N, int64_t K) {
+  return knn_workspace_bytes(B, C, N, K);
+}
+
+int dgcn_knn_graph(const float* x, int64_t B, int64_t C, int64_t N, int64_t stride_b, int64_t stride_c,
+                   const dgcn_dilation* dil, int32_t exclude_self, int64_t* edge_index, int32_t* nbr, void* wsp,
+                   size_t ws_bytes, dgcn_stream_t stream) {
+  KnnArgs a;
+  int rc = fill_knn_args(a, x, B, C, N, stride_b, stride_c, dil, exclude_self);
+  if (rc != DGCN_OK) return rc;
+  if (!edge_index && !nbr) return DGCN_ERR_BAD_ARG;
+  a.epi.edge_index = edge_index;
+  a.epi.nbr = nbr;
+  Workspace ws(wsp, ws_bytes);
+  return launch_knn(a, ws, static_cast<cudaStream_t>(stream));
+}
+
+size_t dgcn_graph_conv_workspace_bytes(int32_t conv, int64_t B, int64_t C_in, int64_t C_out, int64_t N, int64_t k) {
+  return conv_plan_bytes(conv_plan(conv, B, C_in, C_out, N, k, false));
+}
+
+int dgcn_graph_conv_forward(int32_t conv, const float* x, int64_t B, int64_t C_in, int64_t N, int64_t stride_b,
+                            int64_t stride_c, const int64_t* edge_index, const int32_t* nbr, int64_t k,
+                            const dgcn_basic_conv* p, int64_t C_out, float* out, void* wsp, size_t ws_bytes,
+                            dgcn_stream_t stream) {
+  int rc = check_conv_args(conv, x, B, C_in, N, p, C_out, out);
+  if (rc != DGCN_OK) return rc;
+  if ((!edge_index && !nbr) || k <= 0) return DGCN_ERR_BAD_ARG;
+  Workspace ws(wsp, ws_bytes);
+  return conv_forward(conv, x, B, C_in, N, stride_b, stride_c, edge_index, nbr, k, nullptr, p, C_out, out, nullptr,
+                      ws, static_cast<cudaStream_t>(stream));
+}
+
+size_t dgcn_dyn_conv_workspace_bytes(int32_t conv, int64_t B, int64_t C_in, int64_t C_out, int64_t N, int64_t K) {
+  return conv_plan_bytes(conv_plan(conv, B, C_in, C_out, N, K, true)) + knn_workspace_bytes(B, C_in, N, K);
+}
+
+int dgcn_dyn_conv_forward(int32_t conv, const float* x, int64_t B, int64_t C_in, int64_t N, int64_t stride_b,
+                          int64_t stride_c, const dgcn_dilation* dil, const dgcn_basic_conv* p, int64_t C_out,
+                          float* out, int32_t* nbr_out, void* wsp, size_t ws_bytes, dgcn_stream_t stream) {
+  int rc = check_conv_args(conv, x, B, C_in, N, p, C_out, out);
+  if (rc != DGCN_OK) return rc;
+  if (!dil) return DGCN_ERR_BAD_ARG;
+  Workspace ws(wsp, ws_bytes);
+  return conv_forward(conv, x, B, C_in, N, stride_b, stride_c, nullptr, nullptr, 0, dil, p, C_out, out, nbr_out, ws,
+                      static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

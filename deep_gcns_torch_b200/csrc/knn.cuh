@@ -1,0 +1,546 @@
+// Dilated kNN selection kernels (D1/D2 of SURVEY.md 2b) with the fused
+// gather/max consumers (D3/D4) as epilogues.
+//
+//   small path  (K = k*dilation <= 64): one CTA owns 128 queries of a cloud and
+//     streams all candidates through 128x128 fp32 distance tiles; a register
+//     level threshold test feeds per-query candidate buffers in shared memory,
+//     which warps merge into per-query sorted lists.  No (N,N) matrix exists.
+//   large path  (K > 64): distance rows of an L2-sized slab of clouds are
+//     written to the workspace, then one warp per row does an exact
+//     bit-bisection select (in-place compaction in shared memory) of the K-th
+//     key, gathers the K winners in index order and bitonic-sorts them.
+//
+// Ranking is on D = (|x_i|^2 + (-2 x_i.x_j)) + |x_j|^2 in fp32
+// (gcn_lib/dense/torch_edge.py:40-42), ties to the smaller j.
+#pragma once
+#include "common.cuh"
+
+namespace dgcn {
+
+constexpr int MAX_KEEP = 128;       // k (kept neighbours) supported with explicit column lists
+constexpr int SMALL_K_MAX = 64;     // K handled by the fused small path
+constexpr int LARGE_K_MAX = 2048;   // K handled by the slab path
+
+enum EpiMode { EPI_INDEX = 0, EPI_EDGE = 1, EPI_MR = 2 };
+
+// What happens to a query's selected neighbour list.
+struct Epilogue {
+  int mode;
+  int64_t* edge_index;   // (2,B,N,k) or null
+  int32_t* nbr;          // (B,N,k) or null
+  // EPI_EDGE: pq (B,N,2*c_out) node-major: [0,c_out) = (W1-W2)x+b, [c_out,2c_out) = W2 x
+  const float* pq;
+  int c_out;
+  float slope;
+  const float* prelu;
+  int norm;              // dgcn_norm
+  const float* bn_w; const float* bn_b; const float* bn_m; const float* bn_v; float bn_eps;
+  float* out;            // (B,c_out,N): final value, or max_l act() in train mode
+  float* out_min;        // train mode: min_l act()
+  float* partial;        // train mode: [n_cta][2][c_out] sum / sum of squares of act()
+  // EPI_MR: xt (B,N,c_in) node-major copy of x ; r_out (B,c_in,N) = max_l x_j - x_i
+  const float* xt;
+  int c_in;
+  float* r_out;
+};
+
+struct KnnArgs {
+  const float* x; int64_t sb, sc; int B, C, N; int vec;
+  const float* sq;          // (B,N) squared norms
+  int K, k, dilation, has_cols, exclude_self;
+  int cols[MAX_KEEP];
+  Epilogue epi;
+};
+
+__device__ __forceinline__ int keep_rank(const KnnArgs& a, int l) {
+  return a.has_cols ? a.cols[l] : l * a.dilation;
+}
+
+// ---- squared norms -----------------------------------------------------------
+__global__ void sqnorm_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C, int N,
+                              float* __restrict__ sq) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int b = blockIdx.y;
+  if (n >= N) return;
+  const float* p = x + b * sb + n;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) {
+    float v = __ldg(p + c * sc);
+    s = fmaf(v, v, s);
+  }
+  sq[static_cast<int64_t>(b) * N + n] = s;
+}
+
+// ---- per-query consumers -------------------------------------------------------
+// One warp, one query (cloud b, point q, already-selected neighbour ids sel[0..k)).
+// Lane owns channel c (may be >= channel count: then it idles).  Returns max / min
+// over neighbours of act(P_q + Q_j) (EDGE) or of x_j (MR, min unused), plus the
+// sum and sum of squares of act() for batch statistics.
+__device__ __forceinline__ void edge_query(const Epilogue& e, int64_t node0, int q, const int* sel,
+                                           int k, int c, float slope, float& vmax, float& vmin,
+                                           float& s1, float& s2) {
+  vmax = -INFINITY;
+  vmin = INFINITY;
+  if (c >= e.c_out) return;
+  const int ld = 2 * e.c_out;
+  const float p = __ldg(e.pq + (node0 + q) * ld + c);
+  const float* qbase = e.pq + node0 * ld + e.c_out + c;
+  int l = 0;
+  for (; l + 4 <= k; l += 4) {
+    float v0 = __ldg(qbase + static_cast<int64_t>(sel[l + 0]) * ld);
+    float v1 = __ldg(qbase + static_cast<int64_t>(sel[l + 1]) * ld);
+    float v2 = __ldg(qbase + static_cast<int64_t>(sel[l + 2]) * ld);
+    float v3 = __ldg(qbase + static_cast<int64_t>(sel[l + 3]) * ld);
+    float a0 = act_apply(p + v0, slope), a1 = act_apply(p + v1, slope);
+    float a2 = act_apply(p + v2, slope), a3 = act_apply(p + v3, slope);
+    vmax = fmaxf(fmaxf(vmax, a0), fmaxf(a1, fmaxf(a2, a3)));
+    vmin = fminf(fminf(vmin, a0), fminf(a1, fminf(a2, a3)));
+    s1 += (a0 + a1) + (a2 + a3);
+    s2 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+  }
+  for (; l < k; ++l) {
+    float a0 = act_apply(p + __ldg(qbase + static_cast<int64_t>(sel[l]) * ld), slope);
+    vmax = fmaxf(vmax, a0);
+    vmin = fminf(vmin, a0);
+    s1 += a0;
+    s2 += a0 * a0;
+  }
+}
+
+__device__ __forceinline__ float mr_query(const Epilogue& e, int64_t node0, int q, const int* sel,
+                                          int k, int c) {
+  if (c >= e.c_in) return 0.f;
+  const float* base = e.xt + node0 * e.c_in + c;
+  float vmax = -INFINITY;
+  int l = 0;
+  for (; l + 4 <= k; l += 4) {
+    float v0 = __ldg(base + static_cast<int64_t>(sel[l + 0]) * e.c_in);
+    float v1 = __ldg(base + static_cast<int64_t>(sel[l + 1]) * e.c_in);
+    float v2 = __ldg(base + static_cast<int64_t>(sel[l + 2]) * e.c_in);
+    float v3 = __ldg(base + static_cast<int64_t>(sel[l + 3]) * e.c_in);
+    vmax = fmaxf(fmaxf(vmax, v0), fmaxf(v1, fmaxf(v2, v3)));
+  }
+  for (; l < k; ++l) vmax = fmaxf(vmax, __ldg(base + static_cast<int64_t>(sel[l]) * e.c_in));
+  return vmax - __ldg(base + static_cast<int64_t>(q) * e.c_in);
+}
+
+// eval-mode BatchNorm folded to y = s*a + t (gcn_lib/dense/torch_nn.py:28; eps 1e-5)
+__device__ __forceinline__ void bn_affine(const Epilogue& e, int c, float& s, float& t) {
+  s = 1.f;
+  t = 0.f;
+  if (e.norm == DGCN_NORM_BATCH_EVAL && c < e.c_out) {
+    float inv = 1.0f / sqrtf(__ldg(e.bn_v + c) + e.bn_eps);
+    s = (e.bn_w ? __ldg(e.bn_w + c) : 1.f) * inv;
+    t = (e.bn_b ? __ldg(e.bn_b + c) : 0.f) - __ldg(e.bn_m + c) * s;
+  }
+}
+__device__ __forceinline__ float epi_slope(const Epilogue& e) {
+  return e.prelu ? __ldg(e.prelu) : e.slope;
+}
+
+// ---- small path ----------------------------------------------------------------
+constexpr int SM_CAP = 32;                 // candidate buffer entries per query
+constexpr int STAGE_LD = TILE + 1;         // padded staging row (bank-conflict free)
+
+template <int R>
+struct SmallSmem {
+  static constexpr int KP = 32 * R;
+  TileSmem tile;                           // 32 KB, reused as output staging
+  uint64_t list[TILE * KP];                // sorted keys per query
+  uint64_t buf[TILE * SM_CAP];             // unsorted candidates, reused as sel[TILE][2*SM_CAP]
+  uint64_t taukey[TILE];
+  float taud[TILE];
+  int cnt[TILE];
+};
+
+template <int R>
+__device__ __forceinline__ void warp_merge(uint64_t* list, const uint64_t* buf, int m, int K,
+                                           uint64_t* taukey, float* taud, int lane) {
+  uint64_t reg[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) reg[r] = list[r * 32 + lane];
+  for (int e = 0; e < m; ++e) {
+    uint64_t carry = buf[e];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      uint64_t last = shfl_u64(reg[r], 31);
+      if (carry < last) {  // warp-uniform
+        int pos = __popc(__ballot_sync(0xffffffffu, reg[r] < carry));
+        uint64_t up = shfl_up_u64(reg[r], 1);
+        reg[r] = (lane == pos) ? carry : (lane > pos ? up : reg[r]);
+        carry = last;
+      }
+    }
+  }
+  uint64_t tk = KEY_MAX;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    list[r * 32 + lane] = reg[r];
+    if (r == (K - 1) / 32) tk = reg[r];
+  }
+  if (lane == ((K - 1) & 31)) {
+    *taukey = tk;
+    *taud = ordered_to_float(static_cast<uint32_t>(tk >> 32));
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(NTHREADS, R == 1 ? 2 : 1) knn_small_kernel(const KnnArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmallSmem<R>& sm = *reinterpret_cast<SmallSmem<R>*>(smem_raw);
+  constexpr int KP = SmallSmem<R>::KP;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, q0 = blockIdx.x * TILE;
+  const int N = a.N;
+
+  for (int i = tid; i < TILE * KP; i += NTHREADS) sm.list[i] = KEY_MAX;
+  if (tid < TILE) {
+    sm.taukey[tid] = KEY_MAX;
+    sm.taud[tid] = __uint_as_float(0x7FC00000u);  // NaN: "!(d > tau)" admits everything
+    sm.cnt[tid] = 0;
+  }
+  KMajor X = kmajor1(a.x + b * a.sb, a.sc, a.C, N, a.vec != 0);
+  const float* sqb = a.sq + static_cast<int64_t>(b) * N;
+  float sqq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int q = q0 + tile_row(ty, i);
+    sqq[i] = q < N ? __ldg(sqb + q) : 0.f;
+  }
+  __syncthreads();
+
+  for (int j0 = 0; j0 < N; j0 += TILE) {
+    float acc[8][8];
+    tile_product(sm.tile, X, q0, X, j0, acc);
+    float sqj[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int jg = j0 + tile_col(tx, j);
+      sqj[j] = jg < N ? __ldg(sqb + jg) : 0.f;
+    }
+    // register-level threshold test
+    uint64_t pend = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ql = tile_row(ty, i);
+      const int qg = q0 + ql;
+      const float tq = sm.taud[ql];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int jg = j0 + tile_col(tx, j);
+        float d = (sqq[i] + (-2.0f * acc[i][j])) + sqj[j];
+        acc[i][j] = d;
+        bool ok = !(d > tq) && (jg < N) && (qg < N) && !(a.exclude_self && jg == qg);
+        if (ok) pend |= (1ull << (i * 8 + j));
+      }
+    }
+    int more = __syncthreads_or(pend != 0);
+    while (more) {
+      if (pend) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (pend & (1ull << (i * 8 + j))) {
+              const int ql = tile_row(ty, i);
+              uint64_t key = make_key(acc[i][j], static_cast<uint32_t>(j0 + tile_col(tx, j)));
+              if (key < sm.taukey[ql]) {
+                int slot = atomicAdd(&sm.cnt[ql], 1);
+                if (slot < SM_CAP) {
+                  sm.buf[ql * SM_CAP + slot] = key;
+                  pend &= ~(1ull << (i * 8 + j));
+                }
+              } else {
+                pend &= ~(1ull << (i * 8 + j));
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      for (int qq = 0; qq < TILE / 8; ++qq) {
+        const int ql = warp * (TILE / 8) + qq;
+        const int c = sm.cnt[ql];
+        if (c > 0) {
+          warp_merge<R>(&sm.list[ql * KP], &sm.buf[ql * SM_CAP], min(c, SM_CAP), a.K, &sm.taukey[ql],
+                        &sm.taud[ql], lane);
+          __syncwarp();
+          if (lane == 0) sm.cnt[ql] = 0;
+        }
+      }
+      more = __syncthreads_or(pend != 0);
+    }
+  }
+
+  // ---- epilogue: selected ranks -> neighbour ids ---------------------------------
+  const Epilogue& e = a.epi;
+  const int k = a.k;
+  int* sel = reinterpret_cast<int*>(sm.buf);        // [TILE][2*SM_CAP]
+  constexpr int SEL_LD = 2 * SM_CAP;
+  const int64_t node0 = static_cast<int64_t>(b) * N;
+  for (int qq = 0; qq < TILE / 8; ++qq) {
+    const int ql = warp * (TILE / 8) + qq;
+    const int qg = q0 + ql;
+    for (int l = lane; l < k; l += 32) {
+      int idx = static_cast<int>(static_cast<uint32_t>(sm.list[ql * KP + keep_rank(a, l)]));
+      sel[ql * SEL_LD + l] = idx;
+      if (qg < N) {
+        int64_t o = (node0 + qg) * k + l;
+        if (e.nbr) e.nbr[o] = idx;
+        if (e.edge_index) {
+          e.edge_index[o] = idx;
+          e.edge_index[static_cast<int64_t>(a.B) * N * k + o] = qg;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (e.mode == EPI_INDEX) return;
+
+  float* stage_max = reinterpret_cast<float*>(&sm.tile);     // [32][STAGE_LD]
+  float* stage_min = reinterpret_cast<float*>(sm.list);      // [32][STAGE_LD]
+  float* red = stage_min + 32 * STAGE_LD;                    // [8][2][32] stat partials
+  const bool train = (e.mode == EPI_EDGE && e.norm == DGCN_NORM_BATCH_TRAIN);
+  const int nch = (e.mode == EPI_EDGE) ? e.c_out : e.c_in;
+  const float slope = (e.mode == EPI_EDGE) ? epi_slope(e) : 0.f;
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  for (int c0 = 0; c0 < nch; c0 += 32) {
+    const int c = c0 + lane;
+    float s1 = 0.f, s2 = 0.f, bs = 1.f, bt = 0.f;
+    if (e.mode == EPI_EDGE) bn_affine(e, c, bs, bt);
+    for (int qq = 0; qq < TILE / 8; ++qq) {
+      const int ql = warp * (TILE / 8) + qq;
+      const int qg = q0 + ql;
+      if (qg >= N) continue;
+      if (e.mode == EPI_EDGE) {
+        float vmax, vmin;
+        edge_query(e, node0, qg, &sel[ql * SEL_LD], k, c, slope, vmax, vmin, s1, s2);
+        if (train) {
+          stage_max[lane * STAGE_LD + ql] = vmax;
+          stage_min[lane * STAGE_LD + ql] = vmin;
+        } else {
+          stage_max[lane * STAGE_LD + ql] = bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt);
+        }
+      } else {
+        stage_max[lane * STAGE_LD + ql] = mr_query(e, node0, qg, &sel[ql * SEL_LD], k, c);
+      }
+    }
+    if (train) {
+      red[(warp * 2 + 0) * 32 + lane] = s1;
+      red[(warp * 2 + 1) * 32 + lane] = s2;
+    }
+    __syncthreads();
+    float* dst = (e.mode == EPI_EDGE) ? e.out : e.r_out;
+    for (int i = tid; i < 32 * TILE; i += NTHREADS) {
+      const int cc = i >> 7, ql = i & (TILE - 1);
+      if (c0 + cc < nch && q0 + ql < N) {
+        int64_t o = (static_cast<int64_t>(b) * nch + c0 + cc) * N + q0 + ql;
+        dst[o] = stage_max[cc * STAGE_LD + ql];
+        if (train) e.out_min[o] = stage_min[cc * STAGE_LD + ql];
+      }
+    }
+    if (train && tid < 64) {
+      const int which = tid >> 5, cc = tid & 31;
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += red[(w * 2 + which) * 32 + cc];
+      if (c0 + cc < nch) e.partial[(static_cast<int64_t>(cta) * 2 + which) * nch + c0 + cc] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- large path ------------------------------------------------------------------
+// distance rows of clouds [b0, b0+nb) into ws rows (row = (b-b0)*N + q, ld = ldd)
+__global__ void __launch_bounds__(NTHREADS, 2)
+    dist_rows_kernel(const KnnArgs a, int b0, float* __restrict__ drows, int ldd) {
+  __shared__ TileSmem ts;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int b = b0 + blockIdx.z, q0 = blockIdx.y * TILE, j0 = blockIdx.x * TILE;
+  const int N = a.N;
+  KMajor X = kmajor1(a.x + b * a.sb, a.sc, a.C, N, a.vec != 0);
+  float acc[8][8];
+  tile_product(ts, X, q0, X, j0, acc);
+  const float* sqb = a.sq + static_cast<int64_t>(b) * N;
+  float sqj[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int jg = j0 + tile_col(tx, j);
+    sqj[j] = jg < N ? __ldg(sqb + jg) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int qg = q0 + tile_row(ty, i);
+    if (qg >= N) continue;
+    const float sqq = __ldg(sqb + qg);
+    float* row = drows + (static_cast<int64_t>(blockIdx.z) * N + qg) * ldd;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int jg = j0 + tile_col(tx, h * 4);
+      float4 v;
+      v.x = (sqq + (-2.0f * acc[i][h * 4 + 0])) + sqj[h * 4 + 0];
+      v.y = (sqq + (-2.0f * acc[i][h * 4 + 1])) + sqj[h * 4 + 1];
+      v.z = (sqq + (-2.0f * acc[i][h * 4 + 2])) + sqj[h * 4 + 2];
+      v.w = (sqq + (-2.0f * acc[i][h * 4 + 3])) + sqj[h * 4 + 3];
+      if (jg + 3 < ldd) {
+        *reinterpret_cast<float4*>(row + jg) = v;   // ldd % 4 == 0, pad columns are never read
+      }
+    }
+  }
+}
+
+// warp-level bitonic sort of n (power of two) 64-bit keys in shared memory
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t* s, int n, int lane) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = lane; t < (n >> 1); t += 32) {
+        int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        int j = i | stride;
+        uint64_t va = s[i], vb = s[j];
+        bool up = ((i & size) == 0);
+        if ((va > vb) == up) {
+          s[i] = vb;
+          s[j] = va;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// One warp per query row: exact K smallest (key = ordered distance, index), sorted.
+// dynamic smem per warp: keys[nkeys] (u32) | sk[KP] (u64) | sel[k] (int)
+__global__ void select_rows_kernel(const KnnArgs a, int b0, int nb, const float* __restrict__ drows,
+                                   int ldd, int KP, int nkeys, int warps_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = a.N, K = a.K, k = a.k;
+  const size_t per_warp = static_cast<size_t>(KP) * 8 + static_cast<size_t>(nkeys) * 4 + MAX_KEEP * 4;
+  unsigned char* mine = smem_raw + per_warp * warp;
+  uint64_t* sk = reinterpret_cast<uint64_t*>(mine);
+  uint32_t* keys = reinterpret_cast<uint32_t*>(mine + static_cast<size_t>(KP) * 8);
+  int* sel = reinterpret_cast<int*>(mine + static_cast<size_t>(KP) * 8 + static_cast<size_t>(nkeys) * 4);
+
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * warps_per_cta + warp;
+  if (row >= static_cast<int64_t>(nb) * N) return;   // whole warp exits together
+  const int b = b0 + static_cast<int>(row / N), q = static_cast<int>(row % N);
+  const float* drow = drows + row * ldd;
+
+  // 1. ordered keys of the row + which bits vary at all
+  uint32_t vand = 0xFFFFFFFFu, vor = 0u;
+  for (int i = lane; i < N; i += 32) {
+    uint32_t key = float_to_ordered(__ldg(drow + i));
+    if (a.exclude_self && i == q) key = 0xFFFFFFFFu;
+    keys[i] = key;
+    vand &= key;
+    vor |= key;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vand &= __shfl_xor_sync(0xffffffffu, vand, o);
+    vor |= __shfl_xor_sync(0xffffffffu, vor, o);
+  }
+  __syncwarp();
+  // 2. bit bisection with in-place compaction: afterwards every active key equals T,
+  //    and `need` of them (lowest indices) belong to the K smallest.
+  uint32_t vary = vand ^ vor;
+  int n = N, need = K;
+  uint32_t T = vand;   // bits common to all keys
+  for (int bit = 31; bit >= 0 && n > 0; --bit) {
+    if (!((vary >> bit) & 1u)) continue;
+    int c0 = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      int i = i0 + lane;
+      bool z = (i < n) && !((keys[i] >> bit) & 1u);
+      c0 += __popc(__ballot_sync(0xffffffffu, z));
+    }
+    const bool keep_zero = need <= c0;
+    if (!keep_zero) {
+      need -= c0;
+      T |= (1u << bit);
+    } else {
+      T &= ~(1u << bit);
+    }
+    if (c0 == 0 || c0 == n) continue;   // nothing to drop
+    int w = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      int i = i0 + lane;
+      uint32_t key = (i < n) ? keys[i] : 0u;
+      bool keep = (i < n) && ((((key >> bit) & 1u) == 0u) == keep_zero);
+      unsigned m = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) keys[w + __popc(m & ((1u << lane) - 1u))] = key;
+      w += __popc(m);
+      __syncwarp();
+    }
+    n = w;
+  }
+  // 3. gather the K winners in index order
+  int wl = 0, we = 0;   // running counts: taken so far (all) / equal-to-T taken
+  for (int i0 = 0; i0 < N; i0 += 32) {
+    int i = i0 + lane;
+    uint32_t key = 0xFFFFFFFFu;
+    float d = 0.f;
+    if (i < N) {
+      d = __ldg(drow + i);
+      key = float_to_ordered(d);
+      if (a.exclude_self && i == q) key = 0xFFFFFFFFu;
+    }
+    bool less = (i < N) && key < T;
+    bool eq = (i < N) && key == T && !(a.exclude_self && i == q);
+    unsigned me = __ballot_sync(0xffffffffu, eq);
+    int eq_rank = we + __popc(me & ((1u << lane) - 1u));
+    bool take = less || (eq && eq_rank < need);
+    unsigned mt = __ballot_sync(0xffffffffu, take);
+    if (take) sk[wl + __popc(mt & ((1u << lane) - 1u))] = (static_cast<uint64_t>(key) << 32) | static_cast<uint32_t>(i);
+    wl += __popc(mt);
+    we += __popc(me);
+  }
+  for (int i = wl + lane; i < KP; i += 32) sk[i] = KEY_MAX;
+  __syncwarp();
+  // 4. sort, 5. consume
+  warp_bitonic_sort(sk, KP, lane);
+  const Epilogue& e = a.epi;
+  const int64_t node0 = static_cast<int64_t>(b) * N;
+  for (int l = lane; l < k; l += 32) {
+    int idx = static_cast<int>(static_cast<uint32_t>(sk[keep_rank(a, l)]));
+    sel[l] = idx;
+    int64_t o = (node0 + q) * k + l;
+    if (e.nbr) e.nbr[o] = idx;
+    if (e.edge_index) {
+      e.edge_index[o] = idx;
+      e.edge_index[static_cast<int64_t>(a.B) * N * k + o] = q;
+    }
+  }
+  __syncwarp();
+  if (e.mode == EPI_INDEX) return;
+  if (e.mode == EPI_EDGE) {
+    const float slope = epi_slope(e);
+    const bool train = e.norm == DGCN_NORM_BATCH_TRAIN;
+    for (int c0 = 0; c0 < e.c_out; c0 += 32) {
+      const int c = c0 + lane;
+      float vmax, vmin, s1 = 0.f, s2 = 0.f, bs, bt;
+      bn_affine(e, c, bs, bt);
+      edge_query(e, node0, q, sel, k, c, slope, vmax, vmin, s1, s2);
+      if (c < e.c_out) {
+        int64_t o = (static_cast<int64_t>(b) * e.c_out + c) * N + q;
+        if (train) {
+          e.out[o] = vmax;
+          e.out_min[o] = vmin;
+          // one partial slot per query row: [row][2][c_out]
+          e.partial[(static_cast<int64_t>(node0 + q) * 2 + 0) * e.c_out + c] = s1;
+          e.partial[(static_cast<int64_t>(node0 + q) * 2 + 1) * e.c_out + c] = s2;
+        } else {
+          e.out[o] = bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt);
+        }
+      }
+    }
+  } else {
+    for (int c0 = 0; c0 < e.c_in; c0 += 32) {
+      const int c = c0 + lane;
+      float r = mr_query(e, node0, q, sel, k, c);
+      if (c < e.c_in) e.r_out[(static_cast<int64_t>(b) * e.c_in + c) * N + q] = r;
+    }
+  }
+}
+
+}  // namespace dgcn

@@ -1,0 +1,277 @@
+// Sparse path, forward: fused GENConv message + aggregate + MsgNorm + residual over a
+// CSR-by-destination graph (S2/S3/S4 of SURVEY.md 2b) and the halo row gather.
+//
+// One warp owns one destination row; lanes own channels (VEC consecutive channels per
+// lane per channel block, so a warp reads a source row as one coalesced segment).
+// The softmax family is a single-pass online softmax per (row, channel): running
+// max M of t*msg, running sum S of exp(t*msg - M) and running weighted sum WS.
+#include "common.cuh"
+
+namespace dgcn {
+
+struct AggrArgs {
+  const float* x_src; const float* x_dst; int N, C;
+  const int32_t* rowptr; const int32_t* src; const int32_t* eid; const float* edge_attr;
+  int aggr;
+  float t; const float* t_dev; float p; const float* p_dev; float y; const float* y_dev;
+  float eps; int msg_norm; float msg_scale; const float* msg_scale_dev; int add_residual; int raw;
+  float* out;
+};
+
+template <int VEC>
+struct VecF { float v[VEC]; };
+
+template <int VEC>
+__device__ __forceinline__ VecF<VEC> load_vec(const float* p) {
+  VecF<VEC> r;
+  if (VEC == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1 % VEC] = t.y; r.v[2 % VEC] = t.z; r.v[3 % VEC] = t.w;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+
+// channel owned by (lane, block blk, slot j)
+template <int VEC>
+__device__ __forceinline__ int chan_of(int lane, int blk, int j) { return blk * 32 * VEC + lane * VEC + j; }
+
+template <int VEC, int NBLK, int AGGR>
+__global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= g.N) return;
+  const int C = g.C;
+  const int beg = __ldg(g.rowptr + row), end = __ldg(g.rowptr + row + 1);
+  const int deg = end - beg;
+  const float t = g.t_dev ? __ldg(g.t_dev) : g.t;
+  const float p = g.p_dev ? __ldg(g.p_dev) : g.p;
+  constexpr bool kSoftmax = (AGGR == DGCN_AGGR_SOFTMAX || AGGR == DGCN_AGGR_SOFTMAX_SUM);
+  constexpr bool kPower = (AGGR == DGCN_AGGR_POWER || AGGR == DGCN_AGGR_POWER_SUM);
+
+  float m[NBLK][VEC];
+#pragma unroll
+  for (int blk = 0; blk < NBLK; ++blk) {
+    const int cbase = chan_of<VEC>(lane, blk, 0);
+    const bool live = cbase < C;   // C % VEC == 0 so a lane's VEC channels are all in or all out
+    float M[VEC], S[VEC], W[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      M[j] = -INFINITY;
+      S[j] = 0.f;
+      W[j] = (AGGR == DGCN_AGGR_MAX) ? -INFINITY : 0.f;
+    }
+    if (blk * 32 * VEC < C) {   // warp-uniform: this channel block exists
+      for (int e0 = beg; e0 < end; e0 += 32) {
+        const int cnt = min(32, end - e0);
+        int my_src = 0, my_eid = 0;
+        if (lane < cnt) {
+          my_src = __ldg(g.src + e0 + lane);
+          if (g.edge_attr) my_eid = __ldg(g.eid + e0 + lane);
+        }
+        for (int u0 = 0; u0 < cnt; u0 += 4) {
+          VecF<VEC> xv[4], ev[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int s = __shfl_sync(0xffffffffu, my_src, (u0 + u) & 31);
+            const int ei = __shfl_sync(0xffffffffu, my_eid, (u0 + u) & 31);
+            if (live && u0 + u < cnt) {
+              xv[u] = load_vec<VEC>(g.x_src + static_cast<int64_t>(s) * C + cbase);
+              if (g.edge_attr) ev[u] = load_vec<VEC>(g.edge_attr + static_cast<int64_t>(ei) * C + cbase);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (live && u0 + u < cnt) {
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) {
+                float v = xv[u].v[j];
+                if (g.edge_attr) v += ev[u].v[j];
+                const float msg = g.raw ? v : fmaxf(v, 0.f) + g.eps;   // torch_vertex.py:85
+                if (kSoftmax) {
+                  const float z = msg * t;
+                  const float d = z - M[j];
+                  const float ex = __expf(-fabsf(d));
+                  if (d > 0.f) {            // new running max: rescale what was accumulated
+                    S[j] = fmaf(S[j], ex, 1.f);
+                    W[j] = fmaf(W[j], ex, msg);
+                    M[j] = z;
+                  } else {
+                    S[j] += ex;
+                    W[j] = fmaf(ex, msg, W[j]);
+                  }
+                } else if (kPower) {
+                  const float uu = fminf(fmaxf(msg, 1e-7f), 10.f);  // torch_message.py:69-70
+                  W[j] += __powf(uu, p);
+                } else if (AGGR == DGCN_AGGR_MAX) {
+                  W[j] = fmaxf(W[j], msg);
+                } else {
+                  W[j] += msg;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float r;
+      if (kSoftmax) {
+        r = deg > 0 ? W[j] / S[j] : 0.f;
+      } else if (kPower) {
+        float mean = deg > 0 ? W[j] / static_cast<float>(deg) : 0.f;
+        mean = fminf(fmaxf(mean, 1e-7f), 10.f);                     // torch_message.py:73
+        r = __powf(mean, 1.f / p);
+      } else if (AGGR == DGCN_AGGR_MEAN) {
+        r = deg > 0 ? W[j] / static_cast<float>(deg) : 0.f;
+      } else if (AGGR == DGCN_AGGR_MAX) {
+        r = deg > 0 ? W[j] : 0.f;
+      } else {
+        r = W[j];
+      }
+      m[blk][j] = live ? r : 0.f;
+    }
+  }
+  if (AGGR == DGCN_AGGR_SOFTMAX_SUM || AGGR == DGCN_AGGR_POWER_SUM) {   // torch_message.py:60-63,77-80
+    const float y = g.y_dev ? __ldg(g.y_dev) : g.y;
+    const float sig = 1.f / (1.f + __expf(-y));
+    const float f = deg > 0 ? __powf(static_cast<float>(deg), sig) : 0.f;
+#pragma unroll
+    for (int blk = 0; blk < NBLK; ++blk)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) m[blk][j] *= f;
+  }
+  // MsgNorm (torch_message.py:95-99) + residual (torch_vertex.py:73)
+  float xr[NBLK][VEC];
+  float n2m = 0.f, n2x = 0.f;
+  const bool need_x = g.msg_norm || g.add_residual;
+#pragma unroll
+  for (int blk = 0; blk < NBLK; ++blk) {
+    const int cbase = chan_of<VEC>(lane, blk, 0);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) xr[blk][j] = 0.f;
+    if (need_x && cbase < C) {
+      VecF<VEC> xv = load_vec<VEC>(g.x_dst + static_cast<int64_t>(row) * C + cbase);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) xr[blk][j] = xv.v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      n2m = fmaf(m[blk][j], m[blk][j], n2m);
+      n2x = fmaf(xr[blk][j], xr[blk][j], n2x);
+    }
+  }
+  float f = 1.f;
+  if (g.msg_norm) {
+    n2m = warp_sum(n2m);
+    n2x = warp_sum(n2x);
+    const float sc = g.msg_scale_dev ? __ldg(g.msg_scale_dev) : g.msg_scale;
+    f = sqrtf(n2x) * sc / fmaxf(sqrtf(n2m), 1e-12f);
+  }
+#pragma unroll
+  for (int blk = 0; blk < NBLK; ++blk) {
+    const int cbase = chan_of<VEC>(lane, blk, 0);
+    if (cbase < C) {
+      float o[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = g.add_residual ? fmaf(m[blk][j], f, xr[blk][j]) : m[blk][j] * f;
+      float* dst = g.out + static_cast<int64_t>(row) * C + cbase;
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+      } else {
+        dst[0] = o[0];
+      }
+    }
+  }
+}
+
+template <int VEC, int NBLK>
+static int launch_aggr(const AggrArgs& g, cudaStream_t stream) {
+  const int warps = 8;
+  const unsigned grid = static_cast<unsigned>(ceil_div(g.N, warps));
+#define DGCN_AGGR_CASE(A)                                                                   \
+  case A:                                                                                   \
+    genconv_aggregate_kernel<VEC, NBLK, A><<<grid, warps * 32, 0, stream>>>(g);             \
+    break;
+  switch (g.aggr) {
+    DGCN_AGGR_CASE(DGCN_AGGR_SOFTMAX)
+    DGCN_AGGR_CASE(DGCN_AGGR_SOFTMAX_SUM)
+    DGCN_AGGR_CASE(DGCN_AGGR_POWER)
+    DGCN_AGGR_CASE(DGCN_AGGR_POWER_SUM)
+    DGCN_AGGR_CASE(DGCN_AGGR_ADD)
+    DGCN_AGGR_CASE(DGCN_AGGR_MEAN)
+    DGCN_AGGR_CASE(DGCN_AGGR_MAX)
+    default: return DGCN_ERR_UNSUPPORTED;
+  }
+#undef DGCN_AGGR_CASE
+  DGCN_LAUNCH_CHECK();
+  return DGCN_OK;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ x, int C, const int32_t* __restrict__ rows,
+                                   int64_t R, float* __restrict__ out) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int lane = threadIdx.x & 31;
+  const float* src = x + static_cast<int64_t>(__ldg(rows + r)) * C;
+  float* dst = out + r * C;
+  if ((C & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    for (int c = lane * 4; c < C; c += 128)
+      *reinterpret_cast<float4*>(dst + c) = __ldg(reinterpret_cast<const float4*>(src + c));
+  } else {
+    for (int c = lane; c < C; c += 32) dst[c] = __ldg(src + c);
+  }
+}
+
+}  // namespace dgcn
+
+using namespace dgcn;
+
+extern "C" {
+
+int dgcn_genconv_aggregate(const float* x_src, const float* x_dst, int64_t N, int64_t C, const int32_t* rowptr,
+                           const int32_t* src, const int32_t* eid, const float* edge_attr,
+                           const dgcn_genconv_params* prm, float* out, dgcn_stream_t stream) {
+  if (!x_src || !rowptr || !src || !prm || !out || N < 0 || C <= 0) return DGCN_ERR_BAD_ARG;
+  if (!x_dst && (prm->msg_norm || prm->add_residual)) return DGCN_ERR_BAD_ARG;
+  if (edge_attr && !eid) return DGCN_ERR_BAD_ARG;
+  if (N == 0) return DGCN_OK;
+  if (N > (1ll << 31) - 1) return DGCN_ERR_UNSUPPORTED;
+  AggrArgs g{};
+  g.x_src = x_src; g.x_dst = x_dst; g.N = static_cast<int>(N); g.C = static_cast<int>(C);
+  g.rowptr = rowptr; g.src = src; g.eid = eid; g.edge_attr = edge_attr;
+  g.aggr = prm->aggr;
+  g.t = prm->t; g.t_dev = prm->t_dev; g.p = prm->p; g.p_dev = prm->p_dev; g.y = prm->y; g.y_dev = prm->y_dev;
+  g.eps = prm->eps; g.msg_norm = prm->msg_norm; g.msg_scale = prm->msg_scale; g.msg_scale_dev = prm->msg_scale_dev;
+  g.add_residual = prm->add_residual;
+  g.raw = prm->raw_message;
+  g.out = out;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x_src) | reinterpret_cast<uintptr_t>(x_dst) |
+                         reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(edge_attr)) & 15) == 0;
+  if ((C % 4) == 0 && aligned) {
+    if (C <= 128) return launch_aggr<4, 1>(g, s);
+    if (C <= 256) return launch_aggr<4, 2>(g, s);
+    if (C <= 512) return launch_aggr<4, 4>(g, s);
+    if (C <= 1024) return launch_aggr<4, 8>(g, s);
+    return DGCN_ERR_UNSUPPORTED;
+  }
+  if (C <= 32) return launch_aggr<1, 1>(g, s);
+  if (C <= 64) return launch_aggr<1, 2>(g, s);
+  if (C <= 128) return launch_aggr<1, 4>(g, s);
+  if (C <= 256) return launch_aggr<1, 8>(g, s);
+  return DGCN_ERR_UNSUPPORTED;
+}
+
+int dgcn_gather_rows(const float* x, int64_t C, const int32_t* rows, int64_t R, float* out, dgcn_stream_t stream) {
+  if (!x || !rows || !out || C <= 0 || R < 0) return DGCN_ERR_BAD_ARG;
+  if (R == 0) return DGCN_OK;
+  gather_rows_kernel<<<static_cast<unsigned>(ceil_div(R, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<int>(C), rows, R, out);
+  DGCN_LAUNCH_CHECK();
+  return DGCN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+"""GPU parity of the dense path (kNN graph, EdgeConv2d, MRConv2d, DynConv2d) against
+the golden vectors of the unmodified reference and against oracle/ on seeded inputs.
+Tolerance (BASELINE.json north_star): 1e-3 relative fp32 for features; kNN indices
+exact except fp32 near-ties that the fp64 restatement adjudicates."""
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import dense as od
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-3, 1e-4
+
+
+def _mod_from_golden(c, train=None):
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    m = c.meta
+    mod = D.DynConv2d(m["in_channels"], m["out_channels"], m["k"], m["dilation"], m["conv"], m["act"], m["norm"],
+                      m["bias"])
+    missing = mod.load_state_dict(c.sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    mod = mod.cuda()
+    mod.train(m["training"] if train is None else train)
+    return mod
+
+
+def _adjudicate(x, mine, ref, max_frac=2e-3):
+    n_bad, n_unexplained = od.knn_mismatch_report(x.cpu(), mine.cpu().long(), ref.cpu().long())
+    assert n_unexplained == 0, "kNN index mismatch that is not an fp32 near-tie"
+    assert n_bad <= max_frac * mine.numel()
+    return n_bad
+
+
+DYN = [n for n in gu.names("dense_") if "static" not in n and "grid" not in n]
+
+
+@pytest.mark.parametrize("name", DYN)
+def test_golden_dynconv(name):
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    c = gu.load(name)
+    m, x = c.meta, c.ins["x"].cuda()
+    mod = _mod_from_golden(c)
+    # 1. graph: dilated list and the full sorted K list
+    with torch.no_grad():
+        ei = mod.dilated_knn_graph(x)
+        full = D.dense_knn_matrix(x, m["k"] * m["dilation"])
+    assert ei.dtype == torch.int64 and tuple(ei.shape) == (2,) + tuple(c.outs["nn_idx"].shape)
+    assert torch.equal(ei[1].cpu(), c.outs["center_idx"].long())
+    _adjudicate(x, full[0], c.outs["nn_idx_full"])
+    _adjudicate(x, ei[0], c.outs["nn_idx"])
+    # 2. convolution on the reference's own graph
+    gold_ei = torch.stack((c.outs["nn_idx"].long(), c.outs["center_idx"].long()), 0).cuda()
+    sd_before = {k: v.clone() for k, v in mod.state_dict().items()}
+    with torch.no_grad():
+        y_static = D.GraphConv2d.forward(mod, x, gold_ei)
+    torch.testing.assert_close(y_static.cpu(), c.outs["y"], rtol=RTOL, atol=ATOL)
+    if m["training"]:
+        bn = mod.gconv.nn[2]
+        torch.testing.assert_close(bn.running_mean.cpu(), c.outs["running_mean"], rtol=RTOL, atol=1e-5)
+        torch.testing.assert_close(bn.running_var.cpu(), c.outs["running_var"], rtol=RTOL, atol=1e-5)
+        assert int(bn.num_batches_tracked) == int(c.outs["num_batches_tracked"])
+        mod.load_state_dict(sd_before)
+    # 3. fused dynamic path; rows whose neighbour set differs by an adjudicated near-tie are skipped
+    with torch.no_grad():
+        y_dyn = mod(x)
+    same = (ei[0].cpu().sort(-1).values == c.outs["nn_idx"].long().sort(-1).values).all(-1)   # (B,N)
+    assert same.float().mean() > 0.995
+    if m["training"]:
+        if bool(same.all()):
+            torch.testing.assert_close(y_dyn.cpu(), c.outs["y"], rtol=RTOL, atol=ATOL)
+    else:
+        mask = same.unsqueeze(1).unsqueeze(-1).expand_as(c.outs["y"])
+        torch.testing.assert_close(y_dyn.cpu()[mask], c.outs["y"][mask], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("conv", ["edge", "mr"])
+def test_golden_static_arbitrary_centres(conv):
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    c = gu.load("dense_static_%s_arbitrary_centres" % conv)
+    mod = D.GraphConv2d(10, 14, conv, "relu", "batch", True)
+    mod.load_state_dict(c.sd, strict=True)
+    mod = mod.cuda().eval()
+    with torch.no_grad():
+        y = mod(c.ins["x"].cuda(), c.ins["edge_index"].long().cuda())
+    torch.testing.assert_close(y.cpu(), c.outs["y"], rtol=RTOL, atol=ATOL)
+
+
+def test_grid_ties_bit_exact():
+    """Exact-arithmetic cloud: every evaluation order gives identical fp32 distances, so
+    the kernel must reproduce the (distance, index)-lexicographic order bit for bit."""
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    c = gu.load("dense_knn_grid_ties")
+    x, dist = c.ins["x"], c.outs["dist"]
+    N = dist.shape[-1]
+    key = dist.double() * (4 * N) + torch.arange(N).double()      # distances are multiples of 1/64: exact
+    expect = key.argsort(-1)
+    for K in (1, 7, 32, 33, 64, 65, 100, 128):
+        got = D.dense_knn_matrix(x.cuda(), K)[0].cpu()
+        assert torch.equal(got, expect[..., :K]), K
+        # and it agrees with the reference's list up to permutations inside exact ties
+        gold = c.outs["nn_idx_full"].long()[..., :K]
+        assert torch.equal(dist.gather(2, got), dist.gather(2, gold))
+
+
+SWEEP = [
+    # B, C, N, k, d, conv, act, norm, bias
+    (1, 5, 77, 3, 2, "edge", "relu", "batch", True),
+    (3, 20, 130, 7, 1, "mr", "leakyrelu", "batch", False),
+    (2, 3, 1000, 9, 3, "edge", "prelu", None, True),
+    (2, 33, 257, 16, 4, "edge", "relu", "batch", True),      # K = 64, vector loads off (N % 4 != 0)
+    (2, 64, 512, 20, 5, "edge", "relu", "batch", True),      # K = 100 -> slab path
+    (1, 16, 700, 20, 27, "mr", "relu", "batch", True),       # K = 540 -> slab path
+    (2, 70, 384, 12, 1, "mr", "leakyrelu", None, True),
+    (2, 96, 300, 8, 2, "edge", "relu", "batch", True),       # C_out 40 below
+]
+
+
+@pytest.mark.parametrize("cfg", SWEEP)
+def test_sweep_vs_oracle(cfg):
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    B, C, N, k, d, conv, act, norm, bias = cfg
+    g = torch.Generator().manual_seed(hash(cfg) % 1000)
+    torch.manual_seed(1)
+    co = 40 if C == 96 else 24
+    mod = D.DynConv2d(C, co, k, d, conv, act, norm, bias)
+    for m in mod.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data = torch.randn(co, generator=g) * 0.7 + 0.3
+            m.bias.data = torch.randn(co, generator=g) * 0.2
+            m.running_mean.data = torch.randn(co, generator=g) * 0.3
+            m.running_var.data = torch.rand(co, generator=g) + 0.4
+    x = torch.randn(B, C, N, 1, generator=g)
+    p = od.params_from_module(mod.gconv.nn)
+    ref_full = od.knn_matrix(x, k * d)
+    ref_ei = ref_full[:, :, :, ::d]
+    ref_y = od.graph_conv(x, ref_ei, p, conv, act, norm)
+    mod = mod.cuda().eval()
+    xc = x.cuda()
+    with torch.no_grad():
+        full = D.dense_knn_matrix(xc, k * d)
+        ei = mod.dilated_knn_graph(xc)
+        y_static = mod(xc, ref_ei.cuda())
+        y_dyn = mod(xc)
+    _adjudicate(x, full[0], ref_full[0])
+    assert torch.equal(ei, full[:, :, :, ::d])
+    torch.testing.assert_close(y_static.cpu(), ref_y, rtol=RTOL, atol=ATOL)
+    same = (ei[0].cpu().sort(-1).values == ref_ei[0].sort(-1).values).all(-1)
+    assert same.float().mean() > 0.99
+    mask = same.unsqueeze(1).unsqueeze(-1).expand_as(ref_y)
+    torch.testing.assert_close(y_dyn.cpu()[mask], ref_y[mask], rtol=RTOL, atol=ATOL)
+
+
+def test_noncontiguous_slice_and_exclude_self():
+    """inputs[:, 0:3] is what the model stacks feed the head graph builder
+    (examples/sem_seg_dense/architecture.py:49); DilatedKnnGraph excludes self."""
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    g = torch.Generator().manual_seed(3)
+    inputs = torch.rand(2, 9, 640, 1, generator=g)
+    pos = inputs[:, 0:3]
+    ref = od.knn_matrix(pos.contiguous(), 20)
+    got = D.DenseDilatedKnnGraph(20, 1)(inputs.cuda()[:, 0:3])
+    _adjudicate(pos.contiguous(), got[0], ref[0])
+    ref_x = od.knn_exclude_self(pos.contiguous(), 12)[:, :, :, ::3]
+    got_x = D.DilatedKnnGraph(4, 3)(inputs.cuda()[:, 0:3])
+    assert tuple(got_x.shape) == (2, 2, 640, 4)
+    _adjudicate(pos.contiguous(), got_x[0], ref_x[0])
+    assert not (got_x[0] == got_x[1]).any()
+
+
+def test_stochastic_dilation_consumes_rng_like_reference():
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 8, 200, 1, generator=g)
+    graph = D.DenseDilatedKnnGraph(5, 4, stochastic=True, epsilon=1.0).train()
+    torch.manual_seed(9)
+    got = graph(x.cuda())
+    torch.manual_seed(9)
+    ref = od.dilated_knn_graph(x, 5, 4, stochastic=True, epsilon=1.0, training=True)
+    after_ref = torch.rand(1)
+    torch.manual_seed(9)
+    graph(x.cuda())
+    assert torch.equal(torch.rand(1), after_ref)          # same number of host draws
+    _adjudicate(x, got[0], ref[0])
+    graph.eval()                                           # eval: regular dilation, still one draw
+    torch.manual_seed(9)
+    got_eval = graph(x.cuda())
+    assert torch.equal(got_eval.cpu()[0], od.knn_matrix(x, 20)[0][:, :, ::4])
+
+
+def test_errors_mirror_reference():
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    with pytest.raises(NotImplementedError):
+        D.GraphConv2d(4, 4, conv="gat")
+    with pytest.raises(RuntimeError):
+        D.dense_knn_matrix(torch.randn(1, 4, 8, 1).cuda(), 9)      # k > N, torch.topk raises too
+    with pytest.raises(RuntimeError):
+        D.dense_knn_matrix(torch.randn(1, 4, 8, 1), 3)             # CPU tensor: no fallback
+
+
+def test_headline_shape_properties():
+    """BASELINE shape B=16 N=4096 k=20 C=64: size-independent properties + an oracle
+    cross-check on two of the clouds (the oracle needs ~0.2 s per cloud)."""
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    g = torch.Generator().manual_seed(0)
+    torch.manual_seed(0)
+    x = torch.randn(16, 64, 4096, 1, generator=g)
+    mod = D.DynConv2d(64, 64, 20, 1, "edge", "relu", "batch", True).cuda().eval()
+    xc = x.cuda()
+    with torch.no_grad():
+        ei = mod.dilated_knn_graph(xc)
+        y1 = mod(xc)
+        y2 = mod(xc)
+        y_static = mod(xc, ei)
+    assert torch.equal(y1, y2)                                   # deterministic / re-entrant
+    assert torch.equal(y1, y_static)                             # fused == graph-then-conv
+    nn_idx = ei[0]
+    assert torch.equal(nn_idx[..., 0], torch.arange(4096, device="cuda").expand(16, -1))   # self first
+    assert int(nn_idx.min()) >= 0 and int(nn_idx.max()) < 4096
+    srt = nn_idx.sort(-1).values
+    assert bool((srt[..., 1:] != srt[..., :-1]).all())           # no duplicate neighbours
+    xt = xc.squeeze(-1).transpose(1, 2).double()                 # sortedness in fp64 on a row sample
+    rows = torch.arange(0, 4096, 97, device="cuda")
+    d = (xt[:, rows].unsqueeze(2) - xt.gather(1, nn_idx[:, rows].reshape(16, -1, 1).expand(-1, -1, 64))
+         .view(16, rows.numel(), 20, 64)).pow(2).sum(-1)
+    assert bool((d[..., 1:] - d[..., :-1] > -1e-3).all())
+    sub = x[:2]
+    ref = od.knn_matrix(sub, 20)
+    _adjudicate(sub, nn_idx[:2], ref[0])
+    p = od.params_from_module(mod.gconv.nn)
+    p = {k: (v.cpu() if torch.is_tensor(v) else {kk: vv.cpu() for kk, vv in v.items()}) for k, v in p.items()}
+    ref_y = od.graph_conv(sub, ref, p, "edge", "relu", "batch")
+    same = (nn_idx[:2].cpu().sort(-1).values == ref[0].sort(-1).values).all(-1)
+    mask = same.unsqueeze(1).unsqueeze(-1).expand_as(ref_y)
+    torch.testing.assert_close(y1[:2].cpu()[mask], ref_y[mask], rtol=RTOL, atol=ATOL)
