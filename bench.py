@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""Headline benchmark: edges/s of one DynConv2d forward (dilated kNN graph + EdgeConv,
+B=16 N=4096 k=20 C=64 - BASELINE.json's metric shape) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of 16 synthetic clouds
+(1,310,720 edges).  Multi-GPU: the batch dimension is sharded, every rank owns its
+own 16 clouds (weak scaling, no data-path collective - clouds are independent,
+SURVEY.md 8e).  Prints ONE JSON line (rank 0).
+
+`--impl reference` times the reference's CPU algorithm (the oracle port: the
+reference is pure Python/torch, there is nothing to compile into oracle/_ref) on the
+host cores of the box, each step a bounded sample (4 of the 16 clouds).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B, C, N, K_NEIGH, DIL = 16, 64, 4096, 20, 1
+EDGES_PER_STEP = B * N * K_NEIGH
+# compulsory bytes per edge with the graph fused (read x once, write y once)
+ALGO_BYTES_PER_EDGE = (C + C) * 4.0 / K_NEIGH            # 25.6 B
+# fp32 work per edge: distance contraction 2*N*C/k + factorised MLP 2*2C*C/k
+FLOPS_PER_EDGE = 2.0 * N * C / K_NEIGH + 2.0 * 2 * C * C / K_NEIGH
+N_ROTATE = 8                                             # 8 x 16.8 MB inputs = 134 MB > 126 MB L2
+WORKLOAD = "DynConv2d(64,64,k=20,d=1,edge,relu,batch).eval() fwd, x=randn(16,64,4096,1)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(p.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = max(mx, float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_layer(threads):
+    """The reference algorithm (oracle port) and its parameters for the headline layer."""
+    import torch
+    from oracle import dense as od
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(2 * C, C, 1)
+    torch.nn.init.kaiming_normal_(conv.weight)
+    p = {"weight": conv.weight.detach(), "bias": torch.zeros(C),
+         "norm": {"weight": torch.ones(C), "bias": torch.zeros(C), "running_mean": torch.zeros(C),
+                  "running_var": torch.ones(C)}}
+
+    def run(x):
+        with torch.no_grad():
+            return od.dyn_conv(x, p, K_NEIGH, DIL, "edge", "relu", "batch")
+    return run
+
+
+def cpu_sample(gen_seed=0, clouds=4):
+    import torch
+    g = torch.Generator().manual_seed(gen_seed)
+    return torch.randn(clouds, C, N, 1, generator=g)
+
+
+def run_reference(args):
+    """--impl reference: reference CPU path, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = len(os.sched_getaffinity(0))
+    run = oracle_layer(threads)
+    clouds = 4
+    x = cpu_sample(clouds=clouds)
+    edges = clouds * N * K_NEIGH
+    for _ in range(max(args.warmup, 1)):
+        run(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(x)
+    dt = time.perf_counter() - t0
+    value = edges * args.steps / dt
+    sample = "%d of the %d clouds per step (clouds are independent), %d steps" % (clouds, B, args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": "edges/sec EdgeConv fwd (B=16,N=4096,k=20,C=64)", "value": value,
+        "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from deep_gcns_torch_b200 import _native
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+
+    torch.manual_seed(0)
+    mod = D.DynConv2d(C, C, K_NEIGH, DIL, "edge", "relu", "batch", True).to(dev).eval()
+    g = torch.Generator().manual_seed(1000 + rank)
+    host = [torch.randn(B, C, N, 1, generator=g).pin_memory() for _ in range(N_ROTATE)]
+    xs = [h.to(dev) for h in host]
+    host_out = torch.empty(B, C, N, 1).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input throughput ("value") --------------------------------------------
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            mod(xs[i % N_ROTATE])
+        barrier()
+        _native.kernel_timing(True)
+        _native.kernel_timing_read("knn")
+        beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            barrier()
+            beg.record()
+            for i in range(args.steps):
+                mod(xs[i % N_ROTATE])
+            end.record()
+            barrier()
+        ms = beg.elapsed_time(end)
+        knn_ms, knn_n = _native.kernel_timing_read("knn")
+        _native.kernel_timing(False)
+
+        # ---- end to end: pinned host input -> device -> DynConv2d -> host result ----------
+        for i in range(3):
+            host_out.copy_(mod(host[i % N_ROTATE].to(dev, non_blocking=True)), non_blocking=True)
+        barrier()
+        b2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b2.record()
+        for i in range(args.steps):
+            y = mod(host[i % N_ROTATE].to(dev, non_blocking=True))
+            host_out.copy_(y, non_blocking=True)
+        e2.record()
+        barrier()
+        ms_e2e = b2.elapsed_time(e2)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src, sm_max = peaks()
+    kernel_ms = knn_ms / max(knn_n, 1)
+    achieved = EDGES_PER_STEP * ALGO_BYTES_PER_EDGE / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("knn_small_kernel")
+    clk = clocks.summary()
+    fp32_peak = 148 * 128 * 2 * (clk["sm_mhz"] or sm_max) * 1e6 / 1e12
+    out = {
+        "metric": "edges/sec EdgeConv fwd (B=16,N=4096,k=20,C=64)",
+        "value": EDGES_PER_STEP * world * args.steps / (ms * 1e-3),
+        "unit": "edges/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "edges_per_step_per_gpu": EDGES_PER_STEP, "parallelism": "batch-sharded x%d" % world,
+                   "l2": "inputs rotate over %d distinct 16.8 MB batches (134 MB > 126 MB L2)" % N_ROTATE},
+        "e2e": {"value": EDGES_PER_STEP * world * args.steps / (ms_e2e * 1e-3), "unit": "edges/s",
+                "h2d_bytes_per_step": B * C * N * 4, "d2h_bytes_per_step": B * C * N * 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": 4 * args.steps,       # pack_edge_weights, node_pq, sqnorm, knn_small per step
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "knn_small_kernel<1> (fused distance + top-k + gather/max)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / (ms / args.steps),
+                     "note": "algorithmic bytes = 25.6 B/edge x 1,310,720 edges; the kernel is fp32-FMA bound "
+                             "(exact fp32 ranking), see fp32"},
+        "fp32": {"gflop_per_step": EDGES_PER_STEP * FLOPS_PER_EDGE / 1e9,
+                 "achieved_tflops": EDGES_PER_STEP * FLOPS_PER_EDGE / (kernel_ms * 1e-3) / 1e12,
+                 "peak_tflops_at_sampled_clock": fp32_peak},
+    }
+    # ---- CPU baseline: the reference algorithm on this box's host cores, bounded sample ----
+    threads = len(os.sched_getaffinity(0))
+    run = oracle_layer(threads)
+    xc = cpu_sample()
+    run(xc)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t0 < args.cpu_seconds and reps < 50):
+        run(xc)
+        reps += 1
+    dt = time.perf_counter() - t0
+    out["cpu_baseline"] = {"value": xc.shape[0] * N * K_NEIGH * reps / dt, "unit": "edges/s", "cores": threads,
+                           "kind": "port",
+                           "sample": "oracle port of the reference layer on %d of the %d clouds, %d repeats, %.1f s"
+                                     % (xc.shape[0], B, reps, dt)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

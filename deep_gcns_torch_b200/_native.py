@@ -84,6 +84,11 @@ def _declare(lib):
     lib.dgcn_genconv_aggregate_backward.restype = ctypes.c_int
     lib.dgcn_genconv_aggregate_backward.argtypes = [vp, vp, c_i64, c_i64, c_i64, vp, vp, vp, vp,
                                                     ctypes.POINTER(GenconvParamsC), c_i32, vp, vp, vp, vp, vp, vp]
+    lib.dgcn_debug_kernel_timing.restype = ctypes.c_int
+    lib.dgcn_debug_kernel_timing.argtypes = [c_i32]
+    lib.dgcn_debug_kernel_timing_read.restype = ctypes.c_int
+    lib.dgcn_debug_kernel_timing_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double),
+                                                  ctypes.POINTER(c_i64)]
     lib.dgcn_gather_rows.restype = ctypes.c_int
     lib.dgcn_gather_rows.argtypes = [vp, c_i64, vp, c_i64, vp, vp]
 
@@ -335,3 +340,16 @@ def gather_rows(x, rows):
         out = torch.empty((R, C), dtype=torch.float32, device=x.device)
         _check(lib().dgcn_gather_rows(_ptr(x), C, _ptr(rows), R, _ptr(out), _stream(x.device)), "dgcn_gather_rows")
     return out
+
+
+def kernel_timing(enable):
+    """Switch the event bracket around each path's dominant kernel on/off (bench.py)."""
+    return lib().dgcn_debug_kernel_timing(int(bool(enable)))
+
+
+def kernel_timing_read(tag):
+    """(total_ms, launches) of the bracketed kernel `tag` since the last read."""
+    ms, n = ctypes.c_double(0.0), c_i64(0)
+    _check(lib().dgcn_debug_kernel_timing_read(tag.encode(), ctypes.byref(ms), ctypes.byref(n)),
+           "dgcn_debug_kernel_timing_read")
+    return ms.value, n.value

@@ -29,6 +29,14 @@ void set_last_cuda_error(cudaError_t e, const char* file, int line);
     }                                                              \
   } while (0)
 
+// Optional event bracket around a path's dominant kernel (see dgcn_debug_kernel_timing).
+struct KernelTimer {
+  KernelTimer(cudaStream_t stream, const char* tag);
+  ~KernelTimer();
+  cudaStream_t stream_;
+  void* slot_;
+};
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -140,8 +140,7 @@ __global__ void csr_fill_src_kernel(const int64_t* __restrict__ edge_index, cons
   int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= E) return;
   int64_t s = edge_index[eid[e]];
-  s = s < 0 ? 0 : (s >= N ? N - 1 : s);
-  src[e] = static_cast<int32_t>(s);
+  src[e] = static_cast<int32_t>(s < 0 ? 0 : s);   // sources may index a different row set than N (halo / explicit messages)
 }
 
 struct CsrPlan {

@@ -42,7 +42,10 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream) {
     const size_t smem = sizeof(SmallSmem<1>);
     DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    knn_small_kernel<1><<<grid, NTHREADS, smem, stream>>>(a);
+    {
+      KernelTimer timer(stream, "knn");
+      knn_small_kernel<1><<<grid, NTHREADS, smem, stream>>>(a);
+    }
     DGCN_LAUNCH_CHECK();
     return DGCN_OK;
   }
@@ -50,7 +53,10 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream) {
     const size_t smem = sizeof(SmallSmem<2>);
     DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    knn_small_kernel<2><<<grid, NTHREADS, smem, stream>>>(a);
+    {
+      KernelTimer timer(stream, "knn");
+      knn_small_kernel<2><<<grid, NTHREADS, smem, stream>>>(a);
+    }
     DGCN_LAUNCH_CHECK();
     return DGCN_OK;
   }
@@ -60,13 +66,14 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream) {
   float* drows = ws.take<float>(static_cast<size_t>(nbmax) * N * ldd);
   if (!ws.ok) return DGCN_ERR_WORKSPACE;
   const int KP = next_pow2(K);
-  const size_t per_warp = static_cast<size_t>(KP) * 8 + static_cast<size_t>(N) * 4 + MAX_KEEP * 4;
+  const size_t per_warp = static_cast<size_t>(KP) * 8 + static_cast<size_t>(N) * 4 + static_cast<size_t>((a.k + 31) / 32 * 32) * 4;
   int warps = static_cast<int>((200u << 10) / per_warp);
   if (warps < 1) return DGCN_ERR_UNSUPPORTED;   // a single row does not fit in shared memory
   if (warps > 4) warps = 4;
   const size_t smem = per_warp * warps;
   DGCN_CUDA_TRY(cudaFuncSetAttribute(select_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
+  KernelTimer timer(stream, "knn");
   for (int b0 = 0; b0 < B; b0 += nbmax) {
     const int nb = (B - b0 < nbmax) ? (B - b0) : nbmax;
     dist_rows_kernel<<<dim3(ceil_div(N, TILE), ceil_div(N, TILE), nb), NTHREADS, 0, stream>>>(a, b0, drows, ldd);
@@ -85,7 +92,7 @@ int fill_knn_args(KnnArgs& a, const float* x, int64_t B, int64_t C, int64_t N, i
   if (B > 65535 || N > (1 << 30) || C > (1 << 20)) return DGCN_ERR_UNSUPPORTED;
   const int64_t K = dil->k * dil->dilation;
   if (K > N - (exclude_self ? 1 : 0)) return DGCN_ERR_BAD_ARG;   // torch.topk: k out of range
-  if (dil->k > MAX_KEEP) return DGCN_ERR_UNSUPPORTED;
+  if (dil->cols_host && dil->k > MAX_KEEP) return DGCN_ERR_UNSUPPORTED;
   a.x = x; a.sb = stride_b; a.sc = stride_c;
   a.B = static_cast<int>(B); a.C = static_cast<int>(C); a.N = static_cast<int>(N);
   a.vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && stride_b % 4 == 0 && stride_c % 4 == 0 && N % 4 == 0) ? 1 : 0;

@@ -414,7 +414,7 @@ __global__ void select_rows_kernel(const KnnArgs a, int b0, int nb, const float*
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = a.N, K = a.K, k = a.k;
-  const size_t per_warp = static_cast<size_t>(KP) * 8 + static_cast<size_t>(nkeys) * 4 + MAX_KEEP * 4;
+  const size_t per_warp = static_cast<size_t>(KP) * 8 + static_cast<size_t>(nkeys) * 4 + static_cast<size_t>((k + 31) / 32 * 32) * 4;
   unsigned char* mine = smem_raw + per_warp * warp;
   uint64_t* sk = reinterpret_cast<uint64_t*>(mine);
   uint32_t* keys = reinterpret_cast<uint32_t*>(mine + static_cast<size_t>(KP) * 8);

@@ -195,6 +195,7 @@ static int launch_aggr(const AggrArgs& g, cudaStream_t stream) {
   case A:                                                                                   \
     genconv_aggregate_kernel<VEC, NBLK, A><<<grid, warps * 32, 0, stream>>>(g);             \
     break;
+  KernelTimer timer(stream, "aggregate");
   switch (g.aggr) {
     DGCN_AGGR_CASE(DGCN_AGGR_SOFTMAX)
     DGCN_AGGR_CASE(DGCN_AGGR_SOFTMAX_SUM)

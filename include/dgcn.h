@@ -220,6 +220,15 @@ int dgcn_genconv_aggregate_backward(const float* x_src, const float* x_dst, int6
 int dgcn_gather_rows(const float* x, int64_t C, const int32_t* rows, int64_t R, float* out,
                      dgcn_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Measurement hook (bench.py): when enabled, the dominant kernel of each path
+ * ("knn" = the fused selection kernel(s), "aggregate" = the GENConv kernel) is
+ * bracketed by CUDA events on the launch stream.  _read() synchronises those
+ * events, returns the summed duration and launch count for `tag` and resets it.
+ * --------------------------------------------------------------------- */
+int dgcn_debug_kernel_timing(int32_t enable);
+int dgcn_debug_kernel_timing_read(const char* tag, double* total_ms, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

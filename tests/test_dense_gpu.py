@@ -92,7 +92,7 @@ def test_grid_ties_bit_exact():
     c = gu.load("dense_knn_grid_ties")
     x, dist = c.ins["x"], c.outs["dist"]
     N = dist.shape[-1]
-    key = dist.double() * (4 * N) + torch.arange(N).double()      # distances are multiples of 1/64: exact
+    key = dist.double() * (64 * N) + torch.arange(N).double()     # distances are multiples of 1/64: exact
     expect = key.argsort(-1)
     for K in (1, 7, 32, 33, 64, 65, 100, 128):
         got = D.dense_knn_matrix(x.cuda(), K)[0].cpu()
