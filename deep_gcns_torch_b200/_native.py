@@ -287,7 +287,9 @@ def csr_build(edge_index, num_nodes):
         rc = l.dgcn_csr_build(_ptr(edge_index), E, num_nodes, _ptr(rowptr), _ptr(src), _ptr(eid), _ptr(ws),
                               ws.numel(), _stream(dev))
         _check(rc, "dgcn_csr_build")
-    return rowptr, src[:E], eid[:E]
+    if E == 0:          # keep the 1-element placeholders: a 0-element tensor has a null data_ptr
+        return rowptr, src, eid
+    return rowptr, src, eid
 
 
 def _scalar(prm, name, value):

@@ -146,42 +146,39 @@ template <int R>
 struct SmallSmem {
   static constexpr int KP = 32 * R;
   TileSmem tile;                           // 32 KB, reused as output staging
-  uint64_t list[TILE * KP];                // sorted keys per query
-  uint64_t buf[TILE * SM_CAP];             // unsorted candidates, reused as sel[TILE][2*SM_CAP]
+  uint64_t list[KP * TILE];                // sorted keys, rank-major: list[rank*TILE + query]
+  uint64_t buf[SM_CAP * TILE];             // unsorted candidates, slot-major; reused as sel[TILE][2*SM_CAP]
   uint64_t taukey[TILE];
   float taud[TILE];
   int cnt[TILE];
 };
 
+// One thread per query: insertion of the buffered candidates into the query's sorted
+// list (rank-major layout: a warp's 32 queries hit 32 different bank pairs whatever
+// their ranks).  ~6 warp-instructions per insertion amortised, against ~25 for a
+// warp-cooperative insert of one query at a time.
 template <int R>
-__device__ __forceinline__ void warp_merge(uint64_t* list, const uint64_t* buf, int m, int K,
-                                           uint64_t* taukey, float* taud, int lane) {
-  uint64_t reg[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) reg[r] = list[r * 32 + lane];
-  for (int e = 0; e < m; ++e) {
-    uint64_t carry = buf[e];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      uint64_t last = shfl_u64(reg[r], 31);
-      if (carry < last) {  // warp-uniform
-        int pos = __popc(__ballot_sync(0xffffffffu, reg[r] < carry));
-        uint64_t up = shfl_up_u64(reg[r], 1);
-        reg[r] = (lane == pos) ? carry : (lane > pos ? up : reg[r]);
-        carry = last;
+__device__ __forceinline__ void thread_merge(SmallSmem<R>& sm, int q, int K) {
+  const int c = min(sm.cnt[q], SM_CAP);
+  if (c <= 0) return;
+  uint64_t tau = sm.taukey[q];
+  for (int e = 0; e < c; ++e) {
+    const uint64_t key = sm.buf[e * TILE + q];
+    if (key < tau) {
+      int i = K - 1;
+      while (i > 0) {
+        const uint64_t prev = sm.list[(i - 1) * TILE + q];
+        if (prev < key) break;
+        sm.list[i * TILE + q] = prev;
+        --i;
       }
+      sm.list[i * TILE + q] = key;
+      tau = sm.list[(K - 1) * TILE + q];
     }
   }
-  uint64_t tk = KEY_MAX;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    list[r * 32 + lane] = reg[r];
-    if (r == (K - 1) / 32) tk = reg[r];
-  }
-  if (lane == ((K - 1) & 31)) {
-    *taukey = tk;
-    *taud = ordered_to_float(static_cast<uint32_t>(tk >> 32));
-  }
+  sm.taukey[q] = tau;
+  sm.taud[q] = ordered_to_float(static_cast<uint32_t>(tau >> 32));
+  sm.cnt[q] = 0;
 }
 
 template <int R>
@@ -218,57 +215,62 @@ __global__ void __launch_bounds__(NTHREADS, R == 1 ? 2 : 1) knn_small_kernel(con
       int jg = j0 + tile_col(tx, j);
       sqj[j] = jg < N ? __ldg(sqb + jg) : 0.f;
     }
-    // register-level threshold test
-    uint64_t pend = 0;
+    // register-level threshold test; bit (i*8+j) of (pend_hi:pend_lo) = element still to be placed
+    uint32_t pend_lo = 0, pend_hi = 0;
+    const bool edge_tile = (j0 + TILE > N) || (q0 + TILE > N) || (a.exclude_self && j0 == q0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int ql = tile_row(ty, i);
-      const int qg = q0 + ql;
       const float tq = sm.taud[ql];
+      uint32_t bits = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int jg = j0 + tile_col(tx, j);
         float d = (sqq[i] + (-2.0f * acc[i][j])) + sqj[j];
         acc[i][j] = d;
-        bool ok = !(d > tq) && (jg < N) && (qg < N) && !(a.exclude_self && jg == qg);
-        if (ok) pend |= (1ull << (i * 8 + j));
+        bits |= (!(d > tq) ? 1u : 0u) << j;
       }
+      if (edge_tile) {   // ragged tiles / self exclusion: mask out what may not be selected
+        const int qg = q0 + ql;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int jg = j0 + tile_col(tx, j);
+          if (jg >= N || qg >= N || (a.exclude_self && jg == qg)) bits &= ~(1u << j);
+        }
+      }
+      if (i < 4) pend_lo |= bits << (i * 8);
+      else pend_hi |= bits << ((i - 4) * 8);
     }
-    int more = __syncthreads_or(pend != 0);
+    int more = __syncthreads_or((pend_lo | pend_hi) != 0);
     while (more) {
-      if (pend) {
+      if (pend_lo | pend_hi) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+          uint32_t& word = (i < 4) ? pend_lo : pend_hi;
+          if ((word >> ((i & 3) * 8)) & 0xFFu) {
+            const int ql = tile_row(ty, i);
+            const uint64_t tk = sm.taukey[ql];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (pend & (1ull << (i * 8 + j))) {
-              const int ql = tile_row(ty, i);
-              uint64_t key = make_key(acc[i][j], static_cast<uint32_t>(j0 + tile_col(tx, j)));
-              if (key < sm.taukey[ql]) {
-                int slot = atomicAdd(&sm.cnt[ql], 1);
-                if (slot < SM_CAP) {
-                  sm.buf[ql * SM_CAP + slot] = key;
-                  pend &= ~(1ull << (i * 8 + j));
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t bit = 1u << ((i & 3) * 8 + j);
+              if (word & bit) {
+                uint64_t key = make_key(acc[i][j], static_cast<uint32_t>(j0 + tile_col(tx, j)));
+                if (key < tk) {
+                  int slot = atomicAdd(&sm.cnt[ql], 1);
+                  if (slot < SM_CAP) {
+                    sm.buf[slot * TILE + ql] = key;
+                    word &= ~bit;
+                  }
+                } else {
+                  word &= ~bit;
                 }
-              } else {
-                pend &= ~(1ull << (i * 8 + j));
               }
             }
           }
         }
       }
       __syncthreads();
-      for (int qq = 0; qq < TILE / 8; ++qq) {
-        const int ql = warp * (TILE / 8) + qq;
-        const int c = sm.cnt[ql];
-        if (c > 0) {
-          warp_merge<R>(&sm.list[ql * KP], &sm.buf[ql * SM_CAP], min(c, SM_CAP), a.K, &sm.taukey[ql],
-                        &sm.taud[ql], lane);
-          __syncwarp();
-          if (lane == 0) sm.cnt[ql] = 0;
-        }
-      }
-      more = __syncthreads_or(pend != 0);
+      if (tid < TILE) thread_merge<R>(sm, tid, a.K);
+      more = __syncthreads_or((pend_lo | pend_hi) != 0);
     }
   }
 
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(NTHREADS, R == 1 ? 2 : 1) knn_small_kernel(con
     const int ql = warp * (TILE / 8) + qq;
     const int qg = q0 + ql;
     for (int l = lane; l < k; l += 32) {
-      int idx = static_cast<int>(static_cast<uint32_t>(sm.list[ql * KP + keep_rank(a, l)]));
+      int idx = static_cast<int>(static_cast<uint32_t>(sm.list[keep_rank(a, l) * TILE + ql]));
       sel[ql * SEL_LD + l] = idx;
       if (qg < N) {
         int64_t o = (node0 + qg) * k + l;

@@ -43,8 +43,8 @@ def test_csr_build_is_stable_and_complete():
         ei = torch.stack((torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)))
         rowptr, src, eid = _native.csr_build(ei.cuda(), n)
         order = torch.sort(ei[1], stable=True).indices
-        assert torch.equal(eid.cpu().long(), order)
-        assert torch.equal(src.cpu().long(), ei[0][order])
+        assert torch.equal(eid.cpu().long()[:e], order)
+        assert torch.equal(src.cpu().long()[:e], ei[0][order])
         deg = torch.bincount(ei[1], minlength=n)
         assert torch.equal(rowptr.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), deg.cumsum(0)]))
 
