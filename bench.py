@@ -50,8 +50,9 @@ def peaks():
     if os.path.exists(path):
         with open(path) as fh:
             p = json.load(fh)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(p.get("sm_max_mhz", 1965.0))
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1965.0
+        return (float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(p.get("sm_max_mhz", 1965.0)),
+                float(p.get("bf16_tflops", 1590.0)))
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1965.0, 1590.0
 
 
 class ClockSampler:
@@ -229,14 +230,14 @@ def run_native(args):
             dist.destroy_process_group()
         return
 
-    peak, peak_src, sm_max = peaks()
+    peak, peak_src, sm_max, tensor_peak = peaks()
     kernel_ms = knn_ms / max(knn_n, 1)
     achieved = EDGES_PER_STEP * ALGO_BYTES_PER_EDGE / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("knn_small_kernel")
+            traffic = json.load(fh).get("knn_tc_kernel")
     clk = clocks.summary()
     fp32_peak = 148 * 128 * 2 * (clk["sm_mhz"] or sm_max) * 1e6 / 1e12
     out = {
@@ -250,16 +251,21 @@ def run_native(args):
         "e2e": {"value": EDGES_PER_STEP * world * args.steps / (ms_e2e * 1e-3), "unit": "edges/s",
                 "h2d_bytes_per_step": B * C * N * 4, "d2h_bytes_per_step": B * C * N * 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": 4 * args.steps,       # pack_edge_weights, node_pq, sqnorm, knn_small per step
+        # pack_edge_weights, node_pq, sqnorm, split_bf16, to_node_major, sqmax, knn_tc, knn_exact_rows per step
+        "gpu_launches": 8 * args.steps,
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "knn_small_kernel<1> (fused distance + top-k + gather/max)",
+        "roofline": {"bound": "hbm", "kernel": "knn_tc_kernel<24> (tcgen05 bf16x3 pre-filter + exact fp32 re-rank + "
+                                                 "certificate + fused EdgeConv gather/max)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / (ms / args.steps),
-                     "note": "algorithmic bytes = 25.6 B/edge x 1,310,720 edges; the kernel is fp32-FMA bound "
-                             "(exact fp32 ranking), see fp32"},
-        "fp32": {"gflop_per_step": EDGES_PER_STEP * FLOPS_PER_EDGE / 1e9,
-                 "achieved_tflops": EDGES_PER_STEP * FLOPS_PER_EDGE / (kernel_ms * 1e-3) / 1e12,
-                 "peak_tflops_at_sampled_clock": fp32_peak},
+                     "note": "algorithmic bytes = 25.6 B/edge x 1,310,720 edges (read x once, write y once); the "
+                             "kernel is bound by the CUDA-core top-k filter next to the tensor pipe, not by HBM - "
+                             "see tensor"},
+        "tensor": {"bf16_gflop_per_step": 6 * 2.0 * B * N * N * C / 1e9,     # 6 split products hi/mid/lo
+                   "achieved_tflops": 6 * 2.0 * B * N * N * C / (kernel_ms * 1e-3) / 1e12,
+                   "peak_tflops": tensor_peak, "frac": 6 * 2.0 * B * N * N * C / (kernel_ms * 1e-3) / 1e12 / tensor_peak,
+                   "fp32_equivalent_gflop": EDGES_PER_STEP * FLOPS_PER_EDGE / 1e9,
+                   "fp32_fma_peak_tflops_at_sampled_clock": fp32_peak},
     }
     # ---- CPU baseline: the reference algorithm on this box's host cores, bounded sample ----
     threads = len(os.sched_getaffinity(0))

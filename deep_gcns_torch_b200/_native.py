@@ -89,6 +89,8 @@ def _declare(lib):
     lib.dgcn_debug_kernel_timing_read.restype = ctypes.c_int
     lib.dgcn_debug_kernel_timing_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double),
                                                   ctypes.POINTER(c_i64)]
+    lib.dgcn_debug_set_knn_path.restype = ctypes.c_int
+    lib.dgcn_debug_set_knn_path.argtypes = [c_i32]
     lib.dgcn_gather_rows.restype = ctypes.c_int
     lib.dgcn_gather_rows.argtypes = [vp, c_i64, vp, c_i64, vp, vp]
 
@@ -355,3 +357,8 @@ def kernel_timing_read(tag):
     _check(lib().dgcn_debug_kernel_timing_read(tag.encode(), ctypes.byref(ms), ctypes.byref(n)),
            "dgcn_debug_kernel_timing_read")
     return ms.value, n.value
+
+
+def set_knn_path(path):
+    """'tc' (tcgen05 pre-filter + exact re-rank), 'ffma' (fp32 FMA kernel only) or 'auto'."""
+    return lib().dgcn_debug_set_knn_path({"ffma": 0, "tc": 1, "auto": -1}[path])

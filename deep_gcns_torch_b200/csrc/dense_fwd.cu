@@ -1,8 +1,13 @@
 // Dense path, forward: C ABI entry points dgcn_knn_graph / dgcn_graph_conv_forward /
 // dgcn_dyn_conv_forward and the node-level kernels around the selection kernels.
-#include "knn.cuh"
+#include <stdlib.h>
+#include <string.h>
+#include "knn_tc.cuh"
 
 namespace dgcn {
+
+__global__ void to_node_major_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C, int N,
+                                     float* __restrict__ xt);
 
 // ---- launch helpers for the selection kernels -------------------------------------
 static size_t knn_slab_clouds(int64_t B, int64_t N) {
@@ -14,8 +19,29 @@ static size_t knn_slab_clouds(int64_t B, int64_t N) {
   return static_cast<size_t>(nb);
 }
 
+constexpr int TC_FALLBACK_GRID = 64;   // CTAs (x8 warps) of the exact completion kernel
+
+static bool tc_shape_ok(int64_t C, int64_t N, int64_t K) {
+  return K <= TC_K_MAX && C <= TC_MAX_C && N >= TILE && (N % TILE) == 0;
+}
+static int g_knn_path = -1;   // -1: from env DGCN_KNN_PATH (default tensor cores), 0: fp32 FMA only, 1: tensor cores
+static bool tc_enabled() {
+  if (g_knn_path < 0) {
+    const char* v = getenv("DGCN_KNN_PATH");
+    g_knn_path = (v && strcmp(v, "ffma") == 0) ? 0 : 1;
+  }
+  return g_knn_path == 1;
+}
+
 size_t knn_workspace_bytes(int64_t B, int64_t C, int64_t N, int64_t K) {
   size_t bytes = align_up(static_cast<size_t>(B) * N * 4, 256);
+  if (tc_shape_ok(C, N, K)) {
+    const int64_t cpad = (C + 15) / 16 * 16;
+    bytes += align_up(static_cast<size_t>(B) * 3 * cpad * N * 2, 256);   // bf16 planes
+    bytes += align_up(static_cast<size_t>(B) * N * C * 4, 256);          // node-major copy
+    bytes += align_up(static_cast<size_t>(B) * 4, 256);                  // per-cloud max |x|^2
+    bytes += align_up(static_cast<size_t>(B) * N * 4 + 256, 256);        // fail counter + list
+  }
   if (K > SMALL_K_MAX) {
     const int64_t ldd = (N + 3) / 4 * 4;
     bytes += align_up(knn_slab_clouds(B, N) * N * ldd * 4, 256);
@@ -29,15 +55,74 @@ static int next_pow2(int v) {
   return p;
 }
 
+// Tensor-core pre-filter path (knn_tc.cuh).  xt: node-major copy of x if the caller has one.
+static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const float* xt, int64_t* n_partial) {
+  const int B = a.B, N = a.N, C = a.C, K = a.K;
+  const int cpad = (C + 15) / 16 * 16;
+  __nv_bfloat16* planes = ws.take<__nv_bfloat16>(static_cast<size_t>(B) * 3 * cpad * N);
+  float* xt_own = xt ? nullptr : ws.take<float>(static_cast<size_t>(B) * N * C);
+  float* sqmax = ws.take<float>(static_cast<size_t>(B));
+  int* fail = ws.take<int>(static_cast<size_t>(B) * N + 64);
+  if (!ws.ok) return DGCN_ERR_WORKSPACE;
+  DGCN_CUDA_TRY(cudaMemsetAsync(fail, 0, 256, stream));
+  split_bf16_kernel<<<dim3(ceil_div(N, 256), cpad, B), 256, 0, stream>>>(a.x, a.sb, a.sc, C, cpad, N, planes);
+  DGCN_LAUNCH_CHECK();
+  if (!xt) {
+    to_node_major_kernel<<<dim3(ceil_div(N, 32), ceil_div(C, 32), B), dim3(32, 8), 0, stream>>>(a.x, a.sb, a.sc, C, N,
+                                                                                              xt_own);
+    DGCN_LAUNCH_CHECK();
+    xt = xt_own;
+  }
+  sqmax_kernel<<<B, 256, 0, stream>>>(a.sq, N, sqmax);
+  DGCN_LAUNCH_CHECK();
+  TcArgs t{};
+  t.a = a;
+  t.planes = planes;
+  t.xt = xt;
+  t.sqmax = sqmax;
+  t.Cpad = cpad;
+  t.fail_count = fail;
+  t.fail_list = fail + 64;
+  const dim3 grid(N / TILE, B);
+  const int64_t n_cta = static_cast<int64_t>(grid.x) * grid.y;
+  {
+    KernelTimer timer(stream, "knn");
+    const size_t smem = sizeof(TcSmem) + 1024;
+#define DGCN_TC_LAUNCH(KPV)                                                                                   \
+  do {                                                                                                        \
+    DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_tc_kernel<KPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                       static_cast<int>(smem)));                                              \
+    knn_tc_kernel<KPV><<<grid, TC_THREADS, smem, stream>>>(t);                                                \
+  } while (0)
+    // list length per warpgroup = K + certification margin
+    if (K <= 12) DGCN_TC_LAUNCH(16);
+    else if (K <= 20) DGCN_TC_LAUNCH(24);
+    else if (K <= 28) DGCN_TC_LAUNCH(32);
+    else DGCN_TC_LAUNCH(56);
+#undef DGCN_TC_LAUNCH
+    DGCN_LAUNCH_CHECK();
+    float* extra = a.epi.partial ? a.epi.partial + n_cta * 2 * a.epi.c_out : nullptr;
+    knn_exact_rows_kernel<<<TC_FALLBACK_GRID, 256, 0, stream>>>(a, t.fail_count, t.fail_list, extra);
+    DGCN_LAUNCH_CHECK();
+  }
+  if (n_partial) *n_partial = n_cta + TC_FALLBACK_GRID * 8;
+  return DGCN_OK;
+}
+
 // Runs the selection (+ fused consumer described by a.epi) on `stream`.
-int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream) {
+// n_partial (optional out): number of train-mode statistic rows the chosen path wrote.
+int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partial = nullptr) {
   const int B = a.B, N = a.N, K = a.K;
   float* sq = ws.take<float>(static_cast<size_t>(B) * N);
   if (!ws.ok) return DGCN_ERR_WORKSPACE;
   a.sq = sq;
   sqnorm_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(a.x, a.sb, a.sc, a.C, N, sq);
   DGCN_LAUNCH_CHECK();
+  const bool train_wide = a.epi.mode == EPI_EDGE && a.epi.norm == DGCN_NORM_BATCH_TRAIN && a.epi.c_out > 128;
+  if (tc_enabled() && tc_shape_ok(a.C, N, K) && a.k <= SEL_LD && !train_wide)
+    return launch_knn_tc(a, ws, stream, a.epi.mode == EPI_MR ? a.epi.xt : nullptr, n_partial);
   const dim3 grid(ceil_div(N, TILE), B);
+  if (n_partial) *n_partial = K <= SMALL_K_MAX ? static_cast<int64_t>(grid.x) * grid.y : static_cast<int64_t>(B) * N;
   if (K <= 32) {
     const size_t smem = sizeof(SmallSmem<1>);
     DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -383,7 +468,7 @@ static ConvPlan conv_plan(int conv, int64_t B, int64_t ci, int64_t co, int64_t N
     p.bk = 2 * co;
     p.pq = B * N * 2 * co;
     p.out_min = B * co * N;
-    int64_t tiles = fused ? (K <= SMALL_K_MAX ? ceil_div(N, TILE) * B : B * N) : ceil_div(N, 32) * B;
+    int64_t tiles = fused ? (K <= SMALL_K_MAX ? ceil_div(N, TILE) * B + TC_FALLBACK_GRID * 8 : B * N) : ceil_div(N, 32) * B;
     p.n_partial = tiles;
     p.partial = tiles * 2 * co;
   } else {
@@ -469,7 +554,7 @@ static int conv_forward(int conv, const float* x, int64_t B, int64_t ci, int64_t
       int rc = fill_knn_args(a, x, B, ci, N, sb, sc, dil, 0);
       if (rc != DGCN_OK) return rc;
       a.epi = e;
-      rc = launch_knn(a, ws, stream);
+      rc = launch_knn(a, ws, stream, &pl.n_partial);
       if (rc != DGCN_OK) return rc;
     } else {
       GatherArgs g{e, edge_index, nbr, static_cast<int>(B), static_cast<int>(N), static_cast<int>(k)};
@@ -541,6 +626,12 @@ static int conv_forward(int conv, const float* x, int64_t B, int64_t ci, int64_t
 using namespace dgcn;
 
 extern "C" {
+
+int dgcn_debug_set_knn_path(int32_t path) {
+  int old = dgcn::g_knn_path;
+  dgcn::g_knn_path = path;
+  return old;
+}
 
 size_t dgcn_knn_graph_workspace_bytes(int64_t B, int64_t C, int64_t N, int64_t K) {
   return knn_workspace_bytes(B, C, N, K);

@@ -138,10 +138,96 @@ __device__ __forceinline__ float epi_slope(const Epilogue& e) {
   return e.prelu ? __ldg(e.prelu) : e.slope;
 }
 
-// ---- small path ----------------------------------------------------------------
-constexpr int SM_CAP = 32;                 // candidate buffer entries per query
+// ---- CTA-level consumer of finished neighbour lists --------------------------------------
+// list: rank-major sorted keys (list[rank*TILE + query], low 32 bits = neighbour id) of the
+// TILE queries [q0, q0+TILE) of cloud b.  ok[query] == 0 (when given) marks queries whose
+// list is not final (they are completed by the exact fallback kernel) - nothing is written
+// for them.  sel: int [TILE][SEL_LD] scratch; stage_max / stage_min: float [32][STAGE_LD]
+// (+ 2*NW*32 floats after stage_min) scratch; stage_min may alias `list` (it is only
+// touched after every warp has extracted its ids).  All NW warps of the CTA must call.
+constexpr int SEL_LD = 64;
 constexpr int STAGE_LD = TILE + 1;         // padded staging row (bank-conflict free)
 
+template <int NW>
+__device__ __forceinline__ void cta_epilogue(const KnnArgs& a, int b, int q0, const uint64_t* list,
+                                             const unsigned char* ok, int* sel, float* stage_max,
+                                             float* stage_min, int cta) {
+  const Epilogue& e = a.epi;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = a.N, k = a.k;
+  constexpr int QPW = TILE / NW;            // queries per warp
+  const int64_t node0 = static_cast<int64_t>(b) * N;
+  for (int qq = 0; qq < QPW; ++qq) {
+    const int ql = warp * QPW + qq;
+    const int qg = q0 + ql;
+    const bool live = qg < N && (ok == nullptr || ok[ql]);
+    for (int l = lane; l < k; l += 32) {
+      int idx = static_cast<int>(static_cast<uint32_t>(list[keep_rank(a, l) * TILE + ql]));
+      sel[ql * SEL_LD + l] = idx;
+      if (live) {
+        int64_t o = (node0 + qg) * k + l;
+        if (e.nbr) e.nbr[o] = idx;
+        if (e.edge_index) {
+          e.edge_index[o] = idx;
+          e.edge_index[static_cast<int64_t>(a.B) * N * k + o] = qg;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (e.mode == EPI_INDEX) return;
+
+  float* red = stage_min + 32 * STAGE_LD;                    // [NW][2][32] stat partials
+  const bool train = (e.mode == EPI_EDGE && e.norm == DGCN_NORM_BATCH_TRAIN);
+  const int nch = (e.mode == EPI_EDGE) ? e.c_out : e.c_in;
+  const float slope = (e.mode == EPI_EDGE) ? epi_slope(e) : 0.f;
+  for (int c0 = 0; c0 < nch; c0 += 32) {
+    const int c = c0 + lane;
+    float s1 = 0.f, s2 = 0.f, bs = 1.f, bt = 0.f;
+    if (e.mode == EPI_EDGE) bn_affine(e, c, bs, bt);
+    for (int qq = 0; qq < QPW; ++qq) {
+      const int ql = warp * QPW + qq;
+      const int qg = q0 + ql;
+      if (qg >= N || (ok != nullptr && !ok[ql])) continue;
+      if (e.mode == EPI_EDGE) {
+        float vmax, vmin;
+        edge_query(e, node0, qg, &sel[ql * SEL_LD], k, c, slope, vmax, vmin, s1, s2);
+        if (train) {
+          stage_max[lane * STAGE_LD + ql] = vmax;
+          stage_min[lane * STAGE_LD + ql] = vmin;
+        } else {
+          stage_max[lane * STAGE_LD + ql] = bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt);
+        }
+      } else {
+        stage_max[lane * STAGE_LD + ql] = mr_query(e, node0, qg, &sel[ql * SEL_LD], k, c);
+      }
+    }
+    if (train) {
+      red[(warp * 2 + 0) * 32 + lane] = s1;
+      red[(warp * 2 + 1) * 32 + lane] = s2;
+    }
+    __syncthreads();
+    float* dst = (e.mode == EPI_EDGE) ? e.out : e.r_out;
+    for (int i = tid; i < 32 * TILE; i += NW * 32) {
+      const int cc = i >> 7, ql = i & (TILE - 1);
+      if (c0 + cc < nch && q0 + ql < N && (ok == nullptr || ok[ql])) {
+        int64_t o = (static_cast<int64_t>(b) * nch + c0 + cc) * N + q0 + ql;
+        dst[o] = stage_max[cc * STAGE_LD + ql];
+        if (train) e.out_min[o] = stage_min[cc * STAGE_LD + ql];
+      }
+    }
+    if (train && tid < 64) {
+      const int which = tid >> 5, cc = tid & 31;
+      float s = 0.f;
+      for (int w = 0; w < NW; ++w) s += red[(w * 2 + which) * 32 + cc];
+      if (c0 + cc < nch) e.partial[(static_cast<int64_t>(cta) * 2 + which) * nch + c0 + cc] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- small path ----------------------------------------------------------------
+constexpr int SM_CAP = 32;                 // candidate buffer entries per query
 template <int R>
 struct SmallSmem {
   static constexpr int KP = 32 * R;
@@ -274,81 +360,10 @@ __global__ void __launch_bounds__(NTHREADS, R == 1 ? 2 : 1) knn_small_kernel(con
     }
   }
 
-  // ---- epilogue: selected ranks -> neighbour ids ---------------------------------
-  const Epilogue& e = a.epi;
-  const int k = a.k;
-  int* sel = reinterpret_cast<int*>(sm.buf);        // [TILE][2*SM_CAP]
-  constexpr int SEL_LD = 2 * SM_CAP;
-  const int64_t node0 = static_cast<int64_t>(b) * N;
-  for (int qq = 0; qq < TILE / 8; ++qq) {
-    const int ql = warp * (TILE / 8) + qq;
-    const int qg = q0 + ql;
-    for (int l = lane; l < k; l += 32) {
-      int idx = static_cast<int>(static_cast<uint32_t>(sm.list[keep_rank(a, l) * TILE + ql]));
-      sel[ql * SEL_LD + l] = idx;
-      if (qg < N) {
-        int64_t o = (node0 + qg) * k + l;
-        if (e.nbr) e.nbr[o] = idx;
-        if (e.edge_index) {
-          e.edge_index[o] = idx;
-          e.edge_index[static_cast<int64_t>(a.B) * N * k + o] = qg;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (e.mode == EPI_INDEX) return;
-
-  float* stage_max = reinterpret_cast<float*>(&sm.tile);     // [32][STAGE_LD]
-  float* stage_min = reinterpret_cast<float*>(sm.list);      // [32][STAGE_LD]
-  float* red = stage_min + 32 * STAGE_LD;                    // [8][2][32] stat partials
-  const bool train = (e.mode == EPI_EDGE && e.norm == DGCN_NORM_BATCH_TRAIN);
-  const int nch = (e.mode == EPI_EDGE) ? e.c_out : e.c_in;
-  const float slope = (e.mode == EPI_EDGE) ? epi_slope(e) : 0.f;
-  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-  for (int c0 = 0; c0 < nch; c0 += 32) {
-    const int c = c0 + lane;
-    float s1 = 0.f, s2 = 0.f, bs = 1.f, bt = 0.f;
-    if (e.mode == EPI_EDGE) bn_affine(e, c, bs, bt);
-    for (int qq = 0; qq < TILE / 8; ++qq) {
-      const int ql = warp * (TILE / 8) + qq;
-      const int qg = q0 + ql;
-      if (qg >= N) continue;
-      if (e.mode == EPI_EDGE) {
-        float vmax, vmin;
-        edge_query(e, node0, qg, &sel[ql * SEL_LD], k, c, slope, vmax, vmin, s1, s2);
-        if (train) {
-          stage_max[lane * STAGE_LD + ql] = vmax;
-          stage_min[lane * STAGE_LD + ql] = vmin;
-        } else {
-          stage_max[lane * STAGE_LD + ql] = bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt);
-        }
-      } else {
-        stage_max[lane * STAGE_LD + ql] = mr_query(e, node0, qg, &sel[ql * SEL_LD], k, c);
-      }
-    }
-    if (train) {
-      red[(warp * 2 + 0) * 32 + lane] = s1;
-      red[(warp * 2 + 1) * 32 + lane] = s2;
-    }
-    __syncthreads();
-    float* dst = (e.mode == EPI_EDGE) ? e.out : e.r_out;
-    for (int i = tid; i < 32 * TILE; i += NTHREADS) {
-      const int cc = i >> 7, ql = i & (TILE - 1);
-      if (c0 + cc < nch && q0 + ql < N) {
-        int64_t o = (static_cast<int64_t>(b) * nch + c0 + cc) * N + q0 + ql;
-        dst[o] = stage_max[cc * STAGE_LD + ql];
-        if (train) e.out_min[o] = stage_min[cc * STAGE_LD + ql];
-      }
-    }
-    if (train && tid < 64) {
-      const int which = tid >> 5, cc = tid & 31;
-      float s = 0.f;
-      for (int w = 0; w < 8; ++w) s += red[(w * 2 + which) * 32 + cc];
-      if (c0 + cc < nch) e.partial[(static_cast<int64_t>(cta) * 2 + which) * nch + c0 + cc] = s;
-    }
-    __syncthreads();
-  }
+  // ---- epilogue: selected ranks -> neighbour ids -> consumer ------------------------
+  cta_epilogue<NTHREADS / 32>(a, b, q0, sm.list, nullptr, reinterpret_cast<int*>(sm.buf),
+                              reinterpret_cast<float*>(&sm.tile), reinterpret_cast<float*>(sm.list) /* after sel */,
+                              blockIdx.y * gridDim.x + blockIdx.x);
 }
 
 // ---- large path ------------------------------------------------------------------

@@ -1,0 +1,609 @@
+// Tensor-core (tcgen05 / TMEM) path of the dilated kNN selection for K <= 48, C <= 64,
+// N % 128 == 0:  the N x N x C contraction runs on the 5th-gen tensor cores as a CERTIFIED
+// PRE-FILTER, the ranking itself stays exact fp32.
+//
+//   split_kernel      x = hi + mid + lo (three bf16 planes, channel-major like x, channels
+//                     zero-padded to a multiple of 16) - 6 bf16 products hi*hi, hi*mid, mid*hi,
+//                     mid*mid, hi*lo, lo*hi reproduce x_i.x_j to ~2^-22 relative.
+//   knn_tc_kernel     one CTA = 128 queries of a cloud.  Query planes stay resident in shared
+//                     memory; candidate tiles of 128 points stream through a 2-stage cp.async
+//                     ring in the canonical MN-major SWIZZLE_128B layout (x is channel-major =
+//                     MN-major, so no transposition anywhere).  One thread issues the
+//                     tcgen05.mma chain (M=128, N=128, K=16) into one of two TMEM accumulators
+//                     while all 128 threads - thread r owns TMEM lane r = query r - filter the
+//                     other accumulator: approx key = |x_j|^2 - 2*acc against the thread's private
+//                     threshold, survivors go to a private candidate buffer and from there into
+//                     the query's sorted list of the KP best APPROXIMATE keys (no atomics, no
+//                     barriers in the filter).
+//                     Afterwards each thread re-evaluates its KP candidates with the exact fp32
+//                     FMA chain (same values as knn_small_kernel), sorts them, and certifies:
+//                       exact_K-th + eps < approx_KP-th     (eps = bound on |approx - exact|)
+//                     i.e. nothing outside the list can belong to the true K best.  Certified
+//                     queries run the fused consumer; the others are appended to a fail list.
+//   knn_exact_rows_kernel  completes the (rare) uncertified queries with the exact fp32 brute
+//                     force, one warp per query.
+#pragma once
+#include <cuda_bf16.h>
+#include "knn.cuh"
+
+namespace dgcn {
+
+constexpr int TC_MAX_C = 64;
+constexpr int TC_K_MAX = 48;
+constexpr int TC_CAP = 8;          // private candidate buffer entries per query
+
+// ---- PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // bounded spin: a tensor-core pipeline that never signals must trap, not hang the GPU
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {         // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, one thread issues for the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, MN-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
+// [0,14) start>>4 | [16,30) leading-dim byte offset>>4 = stride between 128-byte MN blocks |
+// [32,46) stride byte offset>>4 = stride between groups of 8 K rows | [46,48) version=1 |
+// [61,64) layout = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t mn_block_stride,
+                                                       uint32_t k_group_stride) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((mn_block_stride >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((k_group_stride >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1,
+// b=BF16 [10,13)=1, a_major=MN bit15, b_major=MN bit16, N>>3 [17,23), M>>4 [24,29).
+constexpr uint32_t kIdescBf16MnMn128x128 =
+    (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// ---- operand split ----------------------------------------------------------------------------
+// planes (B, 3, Cpad, N) bf16: x = hi + mid + lo up to 2^-24 relative; channels >= C are zero.
+__global__ void split_bf16_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C, int Cpad, int N,
+                                  __nv_bfloat16* __restrict__ planes) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y, b = blockIdx.z;
+  if (n >= N) return;
+  float v = c < C ? __ldg(x + b * sb + c * sc + n) : 0.f;
+  __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  float r1 = v - __bfloat162float(hi);
+  __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  float r2 = r1 - __bfloat162float(mid);
+  __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+  const int64_t plane = static_cast<int64_t>(Cpad) * N;
+  __nv_bfloat16* base = planes + (static_cast<int64_t>(b) * 3) * plane + static_cast<int64_t>(c) * N + n;
+  base[0] = hi;
+  base[plane] = mid;
+  base[2 * plane] = lo;
+}
+
+// sq (B,N) as in sqnorm_kernel plus the per-cloud maximum (for the certification bound)
+__global__ void sqmax_kernel(const float* __restrict__ sq, int N, float* __restrict__ sqmax) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmaxf(m, sq[static_cast<int64_t>(b) * N + i]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    m = warp_max(m);
+    if (threadIdx.x == 0) sqmax[b] = m;
+  }
+}
+
+// ---- the tensor-core kernel ------------------------------------------------------------------------
+struct TcArgs {
+  KnnArgs a;
+  const __nv_bfloat16* planes;   // (B,3,Cpad,N)
+  const float* xt;               // (B,N,C) node-major fp32 copy (exact re-rank)
+  const float* sqmax;            // (B)
+  int Cpad;
+  int* fail_count;               // device counter
+  int* fail_list;                // (B*N) encoded b*N + q
+};
+
+constexpr int TC_THREADS = 256;                       // two warpgroups, each thread r / r+128 owns query r
+constexpr int TC_FLUSH_AT = 9;                        // flush when any lane of the warp buffered this many
+constexpr int TC_BUF = 16;                            // >= TC_FLUSH_AT - 1 + 8 (checked every 8 columns)
+constexpr int TC_STAGE_BYTES = 3 * 2 * TC_MAX_C * 128;   // 48 KB: 3 planes x 2 MN blocks x 64 rows x 128 B
+
+struct TcSmem {
+  // `work`: operand area while streaming = [queries 48 KB | stage of warpgroup 0 | stage of warpgroup 1],
+  // all canonical MN-major SWIZZLE_128B: [plane][mn_block(2)][Cpad rows][128 B].  Afterwards the same
+  // 144 KB hold the two per-warpgroup candidate lists (front) and sel / staging buffers (back).
+  unsigned char work[3 * TC_STAGE_BYTES];
+  uint64_t cbuf[TC_BUF * TC_THREADS];               // 32 KB private candidate buffers, slot-major
+  float sqj[2][2][TILE];                            // [warpgroup][tile parity][column]
+  float cut[2][TILE];                               // approx key of each list's last entry (inf if not full)
+  float tau_pub[2][TILE];                           // each warpgroup's current admission threshold, read by the other
+  uint64_t mbar[2];
+  uint32_t tmem_base;
+  unsigned char ok[TILE];
+};
+
+// 128 threads of one warpgroup copy one 128-point tile of the three planes into `dst`.
+// Thread r always moves 16-byte chunk (r & 15) of rows (r >> 4) + 8n: the swizzle term and all
+// offsets except the row / plane strides are loop invariant.
+__device__ __forceinline__ void tc_load_tile(unsigned char* dst, const __nv_bfloat16* planes_b, int Cpad, int N,
+                                             int p0, int r) {
+  const int ch = r & 15, row0 = r >> 4;            // row0 in [0,8): (row & 7) == row0 for every row handled
+  const int blk = ch >> 3, c16 = ch & 7;
+  const int64_t plane = static_cast<int64_t>(Cpad) * N;
+  const __nv_bfloat16* src = planes_b + static_cast<int64_t>(row0) * N + p0 + ch * 8;
+  unsigned char* d = dst + blk * (Cpad * 128) + row0 * 128 + ((c16 ^ row0) << 4);
+  const int groups = Cpad >> 3;
+  for (int pl = 0; pl < 3; ++pl) {
+    const __nv_bfloat16* sp = src + pl * plane;
+    unsigned char* dp = d + pl * (2 * Cpad * 128);
+    for (int n = 0; n < groups; ++n) cp_async16(dp + n * 1024, sp + static_cast<int64_t>(n) * 8 * N);
+  }
+}
+
+__device__ __forceinline__ void wg_barrier(int wg) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + wg), "r"(TILE) : "memory");
+}
+
+// Branch-free insertion of (nk, nv) into the ascending register-resident list (k, v):
+// k[i] <- nk < k[i-1] ? k[i-1] : (nk < k[i] ? nk : k[i]).  All indices are compile-time.
+template <int KP>
+__device__ __forceinline__ void reg_insert(uint32_t (&k)[KP], uint32_t (&v)[KP], uint32_t nk, uint32_t nv) {
+  bool lt[KP];
+#pragma unroll
+  for (int i = 0; i < KP; ++i) lt[i] = nk < k[i];
+#pragma unroll
+  for (int i = KP - 1; i > 0; --i) {
+    k[i] = lt[i - 1] ? k[i - 1] : (lt[i] ? nk : k[i]);
+    v[i] = lt[i - 1] ? v[i - 1] : (lt[i] ? nv : v[i]);
+  }
+  k[0] = lt[0] ? nk : k[0];
+  v[0] = lt[0] ? nv : v[0];
+}
+
+template <int KP>
+__global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // SWIZZLE_128B atoms must sit on 1024-byte boundaries of the shared address space
+  unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_al);
+  const KnnArgs& a = t.a;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int wg = tid >> 7, r = tid & (TILE - 1);        // warpgroup, query row = TMEM lane
+  const int b = blockIdx.y, q0 = blockIdx.x * TILE;
+  const int N = a.N, Cpad = t.Cpad;
+  const int plane_bytes = 2 * Cpad * 128;
+  const __nv_bfloat16* planes_b = t.planes + static_cast<int64_t>(b) * 3 * Cpad * N;
+  const float* sqb = a.sq + static_cast<int64_t>(b) * N;
+  unsigned char* qstage = sm.work;
+  unsigned char* mystage = sm.work + (1 + wg) * TC_STAGE_BYTES;
+
+  if (tid == 0) {
+    mbar_init(&sm.mbar[0], 1);
+    mbar_init(&sm.mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&sm.tmem_base, 256);
+  sm.tau_pub[wg][r] = INFINITY;
+  const int ntiles = N / TILE;
+  // queries (warpgroup 0 copies them) + each warpgroup's first candidate tile
+  if (wg == 0) tc_load_tile(qstage, planes_b, Cpad, N, q0, r);
+  if (wg < ntiles) {
+    tc_load_tile(mystage, planes_b, Cpad, N, wg * TILE, r);
+    sm.sqj[wg][0][r] = __ldg(sqb + wg * TILE + r);
+  }
+  cp_async_commit();
+  cp_async_wait_all();
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base + static_cast<uint32_t>(wg * TILE);           // this warpgroup's accumulator
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+
+  const int qg = q0 + r;
+  // the KP best approximate keys of THIS warpgroup's tiles, ascending, in registers
+  uint32_t lk[KP], lv[KP];
+#pragma unroll
+  for (int i = 0; i < KP; ++i) {
+    lk[i] = 0xFFFFFFFFu;
+    lv[i] = 0xFFFFFFFFu;
+  }
+  float tau_own = __uint_as_float(0x7FC00000u);   // NaN admits everything until the list is full
+  uint64_t* const cb0 = sm.cbuf + tid;            // private buffer: slots cb0[0], cb0[TC_THREADS], ...
+  const uint32_t cb_addr0 = smem_u32(cb0);
+  uint32_t cb_addr = cb_addr0;      // next free slot of the private buffer (shared-space byte address)
+  // Warp-synchronous flush: every lane merges ITS buffered candidates in lockstep.
+  auto flush = [&]() {
+    const int cnt = static_cast<int>((cb_addr - cb_addr0) / (TC_THREADS * 8u));
+    int mx = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int e = 0; e < mx; ++e) {
+      uint32_t nk = 0xFFFFFFFFu, nv = 0u;
+      if (e < cnt) {
+        const uint64_t kv = cb0[e * TC_THREADS];     // low word = index, high word = float key bits
+        nk = float_to_ordered(__uint_as_float(static_cast<uint32_t>(kv >> 32)));
+        nv = static_cast<uint32_t>(kv);
+      }
+      if (nk < lk[KP - 1]) reg_insert<KP>(lk, lv, nk, nv);
+    }
+    cb_addr = cb_addr0;
+    tau_own = ordered_to_float(lk[KP - 1]);      // NaN while the list is not full
+    if (tau_own == tau_own) sm.tau_pub[wg][r] = tau_own;
+  };
+
+  for (int tile = wg; tile < ntiles; tile += 2) {
+    const int par = (tile >> 1) & 1;
+    // operands of this tile have landed (own cp.async groups) -> visible to the tensor core
+    cp_async_wait_all();
+    fence_proxy_async();
+    tc_fence_before();
+    wg_barrier(wg);     // also: every thread of the warpgroup finished reading the accumulator of tile-2
+    if (r == 0) {
+      tc_fence_after();
+      const uint32_t abase = smem_u32(qstage), bbase = smem_u32(mystage);
+      const int pa[6] = {0, 0, 1, 1, 0, 2};   // hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi
+      const int pb[6] = {0, 1, 0, 1, 2, 0};
+      uint32_t acc = 0;
+      for (int kk = 0; kk < Cpad / 16; ++kk) {
+#pragma unroll
+        for (int term = 0; term < 6; ++term) {
+          const uint64_t da = umma_desc_mn_sw128(abase + pa[term] * plane_bytes + kk * 2048, Cpad * 128, 1024);
+          const uint64_t db = umma_desc_mn_sw128(bbase + pb[term] * plane_bytes + kk * 2048, Cpad * 128, 1024);
+          umma_bf16(tmem, da, db, kIdescBf16MnMn128x128, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(&sm.mbar[wg]);
+    }
+    mbar_wait(&sm.mbar[wg], static_cast<uint32_t>(par));
+    tc_fence_after();
+    // the stage is free again: prefetch this warpgroup's next tile behind the filter
+    if (tile + 2 < ntiles) {
+      tc_load_tile(mystage, planes_b, Cpad, N, (tile + 2) * TILE, r);
+      cp_async_commit();
+      sm.sqj[wg][par ^ 1][r] = __ldg(sqb + (tile + 2) * TILE + r);
+    }
+    // filter: thread = TMEM lane = query; approx key = |x_j|^2 - 2 x_i.x_j (row-constant |x_i|^2 omitted)
+    const int j0 = tile * TILE;
+    const float4* sqj4 = reinterpret_cast<const float4*>(sm.sqj[wg][par]);
+    const bool diag = a.exclude_self && j0 == q0;
+    // Admission threshold: min of both warpgroups' thresholds.  Each is >= the final KP-th best
+    // approximate key over ALL candidates, so rejecting key >= min cannot lose a top-KP candidate
+    // and "every unlisted candidate has key >= min(final thresholds)" still holds for the certificate.
+    float tau_f = tau_own;
+    {
+      const float other = sm.tau_pub[wg ^ 1][r];
+      if (!(tau_f < other)) tau_f = (tau_f == tau_f) ? fminf(tau_f, other) : other;
+      if (tau_f == INFINITY) tau_f = __uint_as_float(0x7FC00000u);
+    }
+#pragma unroll 1
+    for (int cchunk = 0; cchunk < TILE / 32; ++cchunk) {
+      float v[32];
+      __syncwarp();   // tcgen05.ld is warp-collective
+      tmem_ld32(tmem + lane_base + static_cast<uint32_t>(cchunk * 32), v);
+      if (diag && (r >> 5) == cchunk) {   // self exclusion: only in the diagonal tile, only one column
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i == (r & 31)) v[i] = -INFINITY;   // key becomes +inf
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float4 s0 = sqj4[cchunk * 8 + g * 2], s1 = sqj4[cchunk * 8 + g * 2 + 1];
+        const float sq8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        uint32_t jcur = static_cast<uint32_t>(j0 + cchunk * 32 + g * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float key = fmaf(-2.0f, v[g * 8 + i], sq8[i]);
+          // if (!(key > tau)) { buffer[slot] = (key, index); ++slot; }  - predicated, no branch
+          asm volatile(
+              "{\n"
+              ".reg .pred p;\n"
+              "setp.leu.f32 p, %1, %3;\n"
+              "@p st.shared.v2.b32 [%0], {%2, %1};\n"
+              "@p add.u32 %0, %0, %4;\n"
+              "}"
+              : "+r"(cb_addr)
+              : "f"(key), "r"(jcur), "f"(tau_f), "n"(TC_THREADS * 8)
+              : "memory");
+          ++jcur;
+        }
+        if (__any_sync(0xffffffffu, cb_addr - cb_addr0 >= TC_FLUSH_AT * TC_THREADS * 8u)) {
+          flush();
+          const float other = sm.tau_pub[wg ^ 1][r];
+          tau_f = tau_own;
+          if (!(tau_f < other)) tau_f = (tau_f == tau_f) ? fminf(tau_f, other) : other;
+          if (tau_f == INFINITY) tau_f = __uint_as_float(0x7FC00000u);
+        }
+      }
+    }
+  }
+  flush();
+  tc_fence_before();
+  __syncthreads();   // every MMA has completed, nobody touches operands or TMEM any more
+  if (warp == 0) tmem_dealloc(sm.tmem_base, 256);
+
+  // ---- per list: exact re-rank of the listed candidates (fp32 FMA chain, k ascending) --------------
+  uint64_t* list = reinterpret_cast<uint64_t*>(sm.work) + static_cast<size_t>(wg) * KP * TILE;   // [KP][TILE]
+  sm.cut[wg][r] = (lk[KP - 1] == 0xFFFFFFFFu) ? INFINITY : ordered_to_float(lk[KP - 1]);   // approx key, no |x_i|^2
+  const int C = a.C;
+  const float* xtb = t.xt + static_cast<int64_t>(b) * N * C;
+  float xq[TC_MAX_C];
+#pragma unroll
+  for (int c = 0; c < TC_MAX_C; ++c) xq[c] = c < C ? __ldg(xtb + static_cast<int64_t>(qg) * C + c) : 0.f;
+  const float sqq = __ldg(sqb + qg);
+  {
+    int e = 0;
+#pragma unroll
+    for (int u = 0; u < KP; ++u) {
+      if (lk[u] != 0xFFFFFFFFu || lv[u] != 0xFFFFFFFFu) {
+        const int j = static_cast<int>(lv[u]);
+        const float* xj = xtb + static_cast<int64_t>(j) * C;
+        float acc = 0.f;
+        if ((C & 3) == 0) {
+#pragma unroll
+          for (int c = 0; c < TC_MAX_C; c += 4) {
+            if (c < C) {
+              const float4 w = __ldg(reinterpret_cast<const float4*>(xj + c));
+              acc = fmaf(xq[c], w.x, acc);
+              acc = fmaf(xq[c + 1], w.y, acc);
+              acc = fmaf(xq[c + 2], w.z, acc);
+              acc = fmaf(xq[c + 3], w.w, acc);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < TC_MAX_C; ++c)
+            if (c < C) acc = fmaf(xq[c], __ldg(xj + c), acc);
+        }
+        const float d = (sqq + (-2.0f * acc)) + __ldg(sqb + j);
+        const uint64_t key = make_key(d, static_cast<uint32_t>(j));
+        int i = e;   // insertion by exact key into the exact-sorted prefix [0, e)
+        while (i > 0) {
+          const uint64_t prev = list[(i - 1) * TILE + r];
+          if (prev < key) break;
+          list[i * TILE + r] = prev;
+          --i;
+        }
+        list[i * TILE + r] = key;
+        ++e;
+      }
+    }
+    for (int i = e; i < KP; ++i) list[i * TILE + r] = KEY_MAX;
+  }
+  __syncthreads();
+  // ---- merge the two exact-sorted lists, certify (warpgroup 0, thread = query) -----------------------------
+  uint64_t* la = reinterpret_cast<uint64_t*>(sm.work);
+  uint64_t* lb = la + static_cast<size_t>(KP) * TILE;
+  if (wg == 0) {
+    const int K = a.K;
+    int na = 0, nb = 0;
+    for (int o = 0; o < K; ++o) {          // how many of the K winners come from each list
+      const uint64_t ka = na < KP ? la[na * TILE + r] : KEY_MAX;
+      const uint64_t kb = nb < KP ? lb[nb * TILE + r] : KEY_MAX;
+      if (ka <= kb) ++na; else ++nb;
+    }
+    int ia = na - 1, ib = nb - 1;
+    for (int o = K - 1; o >= 0; --o) {     // in-place merge from the back: o >= ia always
+      const uint64_t ka = ia >= 0 ? la[ia * TILE + r] : 0ull;
+      const uint64_t kb = ib >= 0 ? lb[ib * TILE + r] : 0ull;
+      if (ib < 0 || (ia >= 0 && ka > kb)) {
+        la[o * TILE + r] = ka;
+        --ia;
+      } else {
+        la[o * TILE + r] = kb;
+        --ib;
+      }
+    }
+    const uint64_t kth = la[(K - 1) * TILE + r];
+    bool ok = kth != KEY_MAX;
+    const float cut = fminf(sm.cut[0][r], sm.cut[1][r]);       // every unlisted candidate has approx key >= cut
+    if (ok && cut < INFINITY) {
+      const float dk = ordered_to_float(static_cast<uint32_t>(kth >> 32));
+      const float smax = __ldg(t.sqmax + b);
+      // |approx - exact fp32| <= eps: 6 truncated bf16 products (2^-21 rel. to |x_i||x_j|), ~6*Cpad fp32
+      // tensor-core accumulations and Cpad FMA-chain roundings (2^-23 each), the final additions.
+      const float eps = (2.0f * (4.768e-7f + (7.0f * Cpad + 8.0f) * 1.1921e-7f)) * sqrtf(sqq * smax) +
+                        4.768e-7f * (sqq + smax);
+      ok = (dk + eps < cut + sqq);
+    }
+    sm.ok[r] = ok ? 1 : 0;
+    if (!ok) {
+      const int slot = atomicAdd(t.fail_count, 1);
+      t.fail_list[slot] = b * N + qg;
+    }
+  }
+  __syncthreads();
+  // ---- consumer: sel / staging live at the back of the work area (lists occupy < 78 KB of the front) --------
+  int* sel = reinterpret_cast<int*>(sm.work + 3 * TC_STAGE_BYTES - 66 * 1024);
+  float* stage_max = reinterpret_cast<float*>(sm.work + 3 * TC_STAGE_BYTES - 34 * 1024);
+  float* stage_min = stage_max + 32 * STAGE_LD + 32;
+  cta_epilogue<TC_THREADS / 32>(a, b, q0, la, sm.ok, sel, stage_max, stage_min, blockIdx.y * gridDim.x + blockIdx.x);
+}
+
+// ---- exact completion of uncertified queries ------------------------------------------------------------
+// One warp per failed query: exact fp32 distances to all N candidates (lanes over candidates,
+// FMA chain over channels), warp-wide sorted list of the best 64, then the per-query consumer.
+__global__ void __launch_bounds__(256) knn_exact_rows_kernel(const KnnArgs a, const int* __restrict__ fail_count,
+                                                            const int* __restrict__ fail_list,
+                                                            float* __restrict__ partial_extra) {
+  __shared__ int sel_all[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = gridDim.x * 8;
+  const int total = *fail_count;
+  const Epilogue& e = a.epi;
+  const int N = a.N, C = a.C, K = a.K, k = a.k;
+  float s1acc[4] = {0.f, 0.f, 0.f, 0.f}, s2acc[4] = {0.f, 0.f, 0.f, 0.f};   // c_out <= 128 covered per lane
+  for (int f = blockIdx.x * 8 + warp; f < total; f += nwarps) {
+    const int code = fail_list[f];
+    const int b = code / N, q = code % N;
+    const float* xb = a.x + b * a.sb;
+    const float* sqb = a.sq + static_cast<int64_t>(b) * N;
+    const float sqq = sqb[q];
+    uint64_t r0 = KEY_MAX, r1 = KEY_MAX;   // sorted 64-entry list: r0 = ranks 0..31, r1 = 32..63
+    for (int j0 = 0; j0 < N; j0 += 32) {
+      const int j = j0 + lane;
+      uint64_t key = KEY_MAX;
+      if (j < N && !(a.exclude_self && j == q)) {
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) acc = fmaf(__ldg(xb + c * a.sc + q), __ldg(xb + c * a.sc + j), acc);
+        key = make_key((sqq + (-2.0f * acc)) + sqb[j], static_cast<uint32_t>(j));
+      }
+      const uint64_t worst = shfl_u64(r1, 31);
+      unsigned cand = __ballot_sync(0xffffffffu, key < worst);
+      while (cand) {
+        const int src = __ffs(cand) - 1;
+        cand &= cand - 1;
+        uint64_t carry = shfl_u64(key, src);
+        // insert into r0, evicted element cascades into r1
+        uint64_t last0 = shfl_u64(r0, 31);
+        if (carry < last0) {
+          int pos = __popc(__ballot_sync(0xffffffffu, r0 < carry));
+          uint64_t up = shfl_up_u64(r0, 1);
+          r0 = (lane == pos) ? carry : (lane > pos ? up : r0);
+          carry = last0;
+        }
+        uint64_t last1 = shfl_u64(r1, 31);
+        if (carry < last1) {
+          int pos = __popc(__ballot_sync(0xffffffffu, r1 < carry));
+          uint64_t up = shfl_up_u64(r1, 1);
+          r1 = (lane == pos) ? carry : (lane > pos ? up : r1);
+        }
+      }
+    }
+    (void)K;
+    int* sel = sel_all[warp];
+    const int64_t node0 = static_cast<int64_t>(b) * N;
+    __syncwarp();
+    // ranks are warp-distributed: broadcast them one by one (k <= 64)
+    for (int l = 0; l < k; ++l) {
+      const int rank = keep_rank(a, l);
+      const uint64_t key = (rank < 32) ? shfl_u64(r0, rank) : shfl_u64(r1, rank - 32);
+      if (lane == 0) sel[l] = static_cast<int>(static_cast<uint32_t>(key));
+    }
+    __syncwarp();
+    for (int l = lane; l < k; l += 32) {
+      const int idx = sel[l];
+      const int64_t o = (node0 + q) * k + l;
+      if (e.nbr) e.nbr[o] = idx;
+      if (e.edge_index) {
+        e.edge_index[o] = idx;
+        e.edge_index[static_cast<int64_t>(a.B) * N * k + o] = q;
+      }
+    }
+    if (e.mode == EPI_EDGE) {
+      const float slope = epi_slope(e);
+      const bool train = e.norm == DGCN_NORM_BATCH_TRAIN;
+      for (int c0 = 0, u = 0; c0 < e.c_out; c0 += 32, ++u) {
+        const int c = c0 + lane;
+        float vmax, vmin, s1 = 0.f, s2 = 0.f, bs, bt;
+        bn_affine(e, c, bs, bt);
+        edge_query(e, node0, q, sel, k, c, slope, vmax, vmin, s1, s2);
+        if (c < e.c_out) {
+          const int64_t o = (static_cast<int64_t>(b) * e.c_out + c) * N + q;
+          if (train) {
+            e.out[o] = vmax;
+            e.out_min[o] = vmin;
+            if (u < 4) {
+              s1acc[u] += s1;
+              s2acc[u] += s2;
+            }
+          } else {
+            e.out[o] = bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt);
+          }
+        }
+      }
+    } else if (e.mode == EPI_MR) {
+      for (int c0 = 0; c0 < e.c_in; c0 += 32) {
+        const int c = c0 + lane;
+        const float r = mr_query(e, node0, q, sel, k, c);
+        if (c < e.c_in) e.r_out[(static_cast<int64_t>(b) * e.c_in + c) * N + q] = r;
+      }
+    }
+    __syncwarp();
+  }
+  // train-mode statistics of the queries completed here: one extra partial row per warp
+  if (e.mode == EPI_EDGE && e.norm == DGCN_NORM_BATCH_TRAIN && partial_extra) {
+    const int64_t rowi = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+    for (int u = 0; u < 4; ++u) {
+      const int c = u * 32 + lane;
+      if (c < e.c_out) {
+        partial_extra[(rowi * 2 + 0) * e.c_out + c] = s1acc[u];
+        partial_extra[(rowi * 2 + 1) * e.c_out + c] = s2acc[u];
+      }
+    }
+  }
+}
+
+}  // namespace dgcn

@@ -227,6 +227,9 @@ int dgcn_gather_rows(const float* x, int64_t C, const int32_t* rows, int64_t R, 
  * events, returns the summed duration and launch count for `tag` and resets it.
  * --------------------------------------------------------------------- */
 int dgcn_debug_kernel_timing(int32_t enable);
+/* A/B switch of the small-K selection: 1 = tcgen05 pre-filter + exact re-rank (default),
+ * 0 = fp32 FMA kernel only, -1 = re-read env DGCN_KNN_PATH ("ffma" | "tc").  Returns the old value. */
+int dgcn_debug_set_knn_path(int32_t path);
 int dgcn_debug_kernel_timing_read(const char* tag, double* total_ms, int64_t* launches);
 
 #ifdef __cplusplus

@@ -232,3 +232,57 @@ def test_headline_shape_properties():
     same = (nn_idx[:2].cpu().sort(-1).values == ref[0].sort(-1).values).all(-1)
     mask = same.unsqueeze(1).unsqueeze(-1).expand_as(ref_y)
     torch.testing.assert_close(y1[:2].cpu()[mask], ref_y[mask], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 1024, 20, 1), (2, 3, 512, 20, 1), (1, 32, 256, 16, 3), (3, 9, 384, 9, 2),
+                                   (2, 48, 640, 4, 1), (1, 64, 128, 12, 4)])
+def test_tensor_core_prefilter_equals_exact_fp32_path(shape):
+    """The tcgen05 pre-filter is certified + re-ranked in exact fp32, so its neighbour lists
+    must be IDENTICAL (not just adjudicated-equal) to those of the pure fp32 FMA kernel."""
+    from deep_gcns_torch_b200 import _native
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    B, C, N, k, d = shape
+    g = torch.Generator().manual_seed(N + C)
+    x = torch.randn(B, C, N, 1, generator=g).cuda()
+    x[0, :, 5] = x[0, :, 9]                                   # exact duplicates: forces ties
+    x[0, :, 17] = x[0, :, 9]
+    graph = D.DenseDilatedKnnGraph(k, d)
+    try:
+        _native.set_knn_path("ffma")
+        ref = graph(x)
+        _native.set_knn_path("tc")
+        got = graph(x)
+        assert torch.equal(got, ref)
+        torch.manual_seed(0)
+        mod = D.DynConv2d(C, 24, k, d, "edge", "relu", "batch", True).cuda()
+        for train in (False, True):
+            mod.train(train)
+            _native.set_knn_path("ffma")
+            with torch.no_grad():
+                y_ref = mod(x)
+            _native.set_knn_path("tc")
+            with torch.no_grad():
+                y = mod(x)
+            torch.testing.assert_close(y, y_ref, rtol=1e-5, atol=1e-6)
+    finally:
+        _native.set_knn_path("auto")
+
+
+def test_tensor_core_prefilter_clustered_cloud_falls_back_exactly():
+    """Many near-identical points defeat the certification margin: those queries must be
+    completed by the exact kernel and still match the fp32 path bit for bit."""
+    from deep_gcns_torch_b200 import _native
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    g = torch.Generator().manual_seed(7)
+    centres = torch.randn(1, 16, 8, generator=g)
+    x = centres[:, :, torch.randint(0, 8, (512,), generator=g)] + 1e-6 * torch.randn(1, 16, 512, generator=g)
+    x = x.unsqueeze(-1).cuda()
+    graph = D.DenseDilatedKnnGraph(20, 1)
+    try:
+        _native.set_knn_path("ffma")
+        ref = graph(x)
+        _native.set_knn_path("tc")
+        got = graph(x)
+    finally:
+        _native.set_knn_path("auto")
+    assert torch.equal(got, ref)
