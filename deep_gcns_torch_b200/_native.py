@@ -71,7 +71,7 @@ def _declare(lib):
     lib.dgcn_graph_conv_backward_workspace_bytes.restype = sz
     lib.dgcn_graph_conv_backward_workspace_bytes.argtypes = [c_i32] + [c_i64] * 5
     lib.dgcn_graph_conv_backward.restype = ctypes.c_int
-    lib.dgcn_graph_conv_backward.argtypes = [c_i32, vp, c_i64, c_i64, c_i64, c_i64, c_i64, vp, c_i64,
+    lib.dgcn_graph_conv_backward.argtypes = [c_i32, vp, c_i64, c_i64, c_i64, c_i64, c_i64, vp, vp, c_i64,
                                              ctypes.POINTER(BasicConvC), c_i64, vp, vp, vp, vp, vp, vp, vp,
                                              vp, sz, vp]
     lib.dgcn_csr_build_workspace_bytes.restype = sz
@@ -270,6 +270,46 @@ def dyn_conv_forward(conv, x, prm, k, dilation=1, cols=None, want_nbr=False):
                                      c_out, _ptr(out), _ptr(nbr), _ptr(ws), ws.numel(), _stream(dev))
         _check(rc, "dgcn_dyn_conv_forward")
     return out, nbr
+
+
+def graph_conv_backward(conv, x, prm, grad_out, edge_index=None, nbr=None, need_x=True):
+    """dgcn_graph_conv_backward: dict of gradients (x, weight, bias, bn_weight, bn_bias, prelu)."""
+    _require_cuda(x, grad_out, edge_index, nbr)
+    x3, B, C, N, sb, sc = _dense_view(x)
+    dev = x3.device
+    c_out = prm.weight.shape[0]
+    go = _f32(grad_out).reshape(B, c_out, N)
+    if edge_index is not None:
+        edge_index = edge_index.long().contiguous()
+        k = edge_index.shape[-1]
+    else:
+        nbr = nbr.contiguous()
+        k = nbr.shape[-1]
+    with torch.cuda.device(dev):
+        l = lib()
+        cs = BasicConvC()
+        cs.weight, cs.bias = _ptr(prm.weight), _ptr(prm.bias)
+        cs.act, cs.slope, cs.prelu_weight = prm.act, 0.2, _ptr(prm.prelu_weight)
+        cs.norm = prm.norm
+        cs.bn_weight, cs.bn_bias, cs.bn_eps = _ptr(prm.bn_weight), _ptr(prm.bn_bias), prm.bn_eps
+        if prm.norm == NORM_BATCH_TRAIN:      # statistics of the batch the forward normalised with
+            cs.bn_mean, cs.bn_var = _ptr(prm.batch_mean), _ptr(prm.batch_var)
+        else:
+            cs.bn_mean, cs.bn_var = _ptr(prm.bn_mean), _ptr(prm.bn_var)
+        f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        g = {"x": f(B, C, N) if need_x else None, "weight": f(c_out, 2 * C),
+             "bias": f(c_out) if prm.bias is not None else None,
+             "bn_weight": f(c_out) if prm.norm != NORM_NONE else None,
+             "bn_bias": f(c_out) if prm.norm != NORM_NONE else None,
+             "prelu": f(1) if prm.prelu_weight is not None else None}
+        ws = _workspace(l.dgcn_graph_conv_backward_workspace_bytes(CONV[conv], B, C, c_out, N, k) + 8 * c_out + 256,
+                        dev)
+        rc = l.dgcn_graph_conv_backward(CONV[conv], _ptr(x3), B, C, N, sb, sc, _ptr(edge_index), _ptr(nbr), k,
+                                        ctypes.byref(cs), c_out, _ptr(go), _ptr(g["x"]), _ptr(g["weight"]),
+                                        _ptr(g["bias"]), _ptr(g["bn_weight"]), _ptr(g["bn_bias"]), _ptr(g["prelu"]),
+                                        _ptr(ws), ws.numel(), _stream(dev))
+        _check(rc, "dgcn_graph_conv_backward")
+    return g
 
 
 def csr_build(edge_index, num_nodes):

@@ -143,14 +143,18 @@ int dgcn_dyn_conv_forward(int32_t conv, const float* x, int64_t B, int64_t C_in,
 
 /* Gradient of dgcn_graph_conv_forward w.r.t. x and the BasicConv parameters
  * (what torch autograd derives for torch_vertex.py:16-35 + torch_nn.py:48-58).
- * The graph is the one used in forward (nbr (B,N,k) int32, centre = own
- * index - the kNN graph is non-differentiable, torch_edge.py:53-56).
+ * The graph is the one used in forward (edge_index (2,B,N,k) int64 or nbr
+ * (B,N,k) int32 with centre = own index; the kNN graph itself is
+ * non-differentiable, torch_edge.py:53-56).  With DGCN_NORM_BATCH_TRAIN,
+ * p->bn_mean / p->bn_var must hold the BATCH statistics the forward returned.
+ * grad_x is (B, C_in, N) contiguous.
  * grad_weight (C_out,2*C_in), grad_bias (C_out), grad_bn_weight/bias (C_out),
  * grad_prelu (1) are OVERWRITTEN; any of them may be NULL. */
 size_t dgcn_graph_conv_backward_workspace_bytes(int32_t conv, int64_t B, int64_t C_in,
                                                 int64_t C_out, int64_t N, int64_t k);
 int dgcn_graph_conv_backward(int32_t conv, const float* x, int64_t B, int64_t C_in, int64_t N,
-                             int64_t stride_b, int64_t stride_c, const int32_t* nbr, int64_t k,
+                             int64_t stride_b, int64_t stride_c, const int64_t* edge_index,
+                             const int32_t* nbr, int64_t k,
                              const dgcn_basic_conv* p, int64_t C_out, const float* grad_out,
                              float* grad_x, float* grad_weight, float* grad_bias,
                              float* grad_bn_weight, float* grad_bn_bias, float* grad_prelu,
