@@ -375,6 +375,28 @@ def genconv_aggregate(x_src, x_dst, csr, prm, edge_attr=None):
     return out
 
 
+def genconv_aggregate_backward(x_src, x_dst, csr, prm, grad_out, edge_attr=None, softmax_grad=False,
+                               need_edge_attr=False):
+    """dgcn_genconv_aggregate_backward: (grad_x_src (N_src,C), grad_x_dst (N,C) | None,
+    grad_edge_attr | None, grad_scalars (4) = d/dt, d/dp, d/dy, d/dmsg_scale)."""
+    rowptr, src, eid = csr
+    _require_cuda(x_src, x_dst, grad_out, edge_attr)
+    x_src, x_dst, edge_attr, grad_out = _f32(x_src), _f32(x_dst), _f32(edge_attr), _f32(grad_out)
+    N, C = rowptr.numel() - 1, x_src.shape[1]
+    dev = x_src.device
+    with torch.cuda.device(dev):
+        gsrc = torch.zeros_like(x_src)
+        gdst = torch.empty((N, C), dtype=torch.float32, device=dev) if x_dst is not None else None
+        gea = torch.zeros_like(edge_attr) if (need_edge_attr and edge_attr is not None) else None
+        gsc = torch.zeros(4, dtype=torch.float32, device=dev)
+        rc = lib().dgcn_genconv_aggregate_backward(_ptr(x_src), _ptr(x_dst), N, x_src.shape[0], C, _ptr(rowptr),
+                                                   _ptr(src), _ptr(eid), _ptr(edge_attr), ctypes.byref(prm),
+                                                   int(bool(softmax_grad)), _ptr(grad_out), _ptr(gsrc), _ptr(gdst),
+                                                   _ptr(gea), _ptr(gsc), _stream(dev))
+        _check(rc, "dgcn_genconv_aggregate_backward")
+    return gsrc, gdst, gea, gsc
+
+
 def gather_rows(x, rows):
     _require_cuda(x, rows)
     x = _f32(x)
