@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Model-level timing of BASELINE configs 2 and 3 on one B200 (secondary; bench.py is the
+driver's contract): the reference's model assembly restated on top of the drop-in classes.
+
+  c2  ResGCN-28 (examples/sem_seg_dense/architecture.py:7-56): DenseDilatedKnnGraph + head
+      GraphConv2d + 27 ResDynBlock2d (dilation 1..27) + fusion / prediction BasicConvs,
+      inputs (16, 9, 4096, 1), k=20.
+  c3  DeeperGCN-56 'res+' (examples/ogb/ogbn_arxiv/model.py:80-140): 56 GENConv(128,128,
+      softmax_sg, t=0.1, mlp_layers=1) + BatchNorm1d, synthetic arxiv-shaped graph.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+class ResGCN28(torch.nn.Module):
+    def __init__(self, D, in_channels=9, n_classes=13, k=20, channels=64, n_blocks=28):
+        super().__init__()
+        self.n_blocks = n_blocks
+        self.knn = D.DenseDilatedKnnGraph(k, 1, True, 0.2)
+        self.head = D.GraphConv2d(in_channels, channels, "edge", "relu", "batch", True)
+        self.backbone = torch.nn.Sequential(*[D.ResDynBlock2d(channels, k, 1 + i, "edge", "relu", "batch", True, True, 0.2)
+                                              for i in range(n_blocks - 1)])
+        fusion_dims = channels * n_blocks
+        self.fusion_block = D.BasicConv([fusion_dims, 1024], "relu", "batch", True)
+        self.prediction = torch.nn.Sequential(D.BasicConv([fusion_dims + 1024, 512], "relu", "batch", True),
+                                              D.BasicConv([512, 256], "relu", "batch", True), torch.nn.Dropout(0.3),
+                                              D.BasicConv([256, n_classes], None, None, True))
+
+    def backbone_forward(self, inputs):
+        feats = [self.head(inputs, self.knn(inputs[:, 0:3]))]
+        for i in range(self.n_blocks - 1):
+            feats.append(self.backbone[i](feats[-1]))
+        return feats
+
+    def forward(self, inputs):
+        feats = torch.cat(self.backbone_forward(inputs), dim=1)
+        fusion = torch.max_pool2d(self.fusion_block(feats), kernel_size=[feats.shape[2], feats.shape[3]])
+        fusion = torch.repeat_interleave(fusion, repeats=feats.shape[2], dim=2)
+        return self.prediction(torch.cat((fusion, feats), dim=1)).squeeze(-1)
+
+
+class DeeperGCN(torch.nn.Module):
+    def __init__(self, S, layers=56, hidden=128, in_channels=128, tasks=40):
+        super().__init__()
+        self.enc = torch.nn.Linear(in_channels, hidden)
+        self.gcns = torch.nn.ModuleList(S.GENConv(hidden, hidden, aggr="softmax_sg", t=0.1, mlp_layers=1, norm="batch")
+                                        for _ in range(layers))
+        self.norms = torch.nn.ModuleList(S.norm_layer("batch", hidden) for _ in range(layers))
+        self.pred = torch.nn.Linear(hidden, tasks)
+
+    def forward(self, x, edge_index):
+        h = self.gcns[0](self.enc(x), edge_index)
+        for l in range(1, len(self.gcns)):
+            h = self.gcns[l](F.relu(self.norms[l - 1](h)), edge_index) + h
+        return torch.log_softmax(self.pred(F.relu(self.norms[-1](h))), dim=-1)
+
+
+def timeit(fn, steps=5):
+    fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="c2,c3")
+    a = ap.parse_args()
+    from deep_gcns_torch_b200.gcn_lib import dense as D, sparse as S
+    from oracle import sparse as osp
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    out = {}
+    if "c2" in a.which:
+        torch.manual_seed(0)
+        model = ResGCN28(D).to(dev).eval()
+        inputs = torch.rand(16, 4096, 9, generator=g).transpose(1, 2).unsqueeze(-1).contiguous().to(dev)
+        with torch.no_grad():
+            ms_bb = timeit(lambda: model.backbone_forward(inputs))
+            ms_all = timeit(lambda: model(inputs))
+            per_layer = []
+            feats = model.head(inputs, model.knn(inputs[:, 0:3]))
+            for i in (0, 1, 2, 3, 7, 15, 26):
+                blk = model.backbone[i]
+                per_layer.append({"dilation": i + 1, "K": 20 * (i + 1), "ms": timeit(lambda: blk(feats), 3)})
+        edges = 28 * 16 * 4096 * 20
+        out["c2_resgcn28"] = {"backbone_ms": ms_bb, "model_ms": ms_all, "edges_per_s_backbone": edges / (ms_bb * 1e-3),
+                              "per_layer": per_layer}
+    if "c3" in a.which:
+        N = 169343
+        s, d = torch.randint(0, N, (1166243,), generator=g), torch.randint(0, N, (1166243,), generator=g)
+        ei = osp.to_undirected_with_self_loops(s, d, N).to(dev)
+        x = torch.randn(N, 128, generator=g).to(dev)
+        torch.manual_seed(0)
+        model = DeeperGCN(S).to(dev).eval()
+        with torch.no_grad():
+            ms = timeit(lambda: model(x, ei))
+        out["c3_deepergcn56"] = {"model_ms": ms, "edges_per_s": 56 * ei.shape[1] / (ms * 1e-3), "E": int(ei.shape[1])}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,12 @@ struct AggrArgs {
   float* out;
 };
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int VEC>
 struct VecF { float v[VEC]; };
 
@@ -47,6 +53,7 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
   const int deg = end - beg;
   const float t = g.t_dev ? __ldg(g.t_dev) : g.t;
   const float p = g.p_dev ? __ldg(g.p_dev) : g.p;
+  const float tl = t * 1.4426950408889634f;   // softmax in base 2
   constexpr bool kSoftmax = (AGGR == DGCN_AGGR_SOFTMAX || AGGR == DGCN_AGGR_SOFTMAX_SUM);
   constexpr bool kPower = (AGGR == DGCN_AGGR_POWER || AGGR == DGCN_AGGR_POWER_SUM);
 
@@ -72,42 +79,57 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
         }
         for (int u0 = 0; u0 < cnt; u0 += 4) {
           VecF<VEC> xv[4], ev[4];
+          bool have[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int s = __shfl_sync(0xffffffffu, my_src, (u0 + u) & 31);
-            const int ei = __shfl_sync(0xffffffffu, my_eid, (u0 + u) & 31);
-            if (live && u0 + u < cnt) {
+            int ei = 0;
+            if (g.edge_attr) ei = __shfl_sync(0xffffffffu, my_eid, (u0 + u) & 31);   // warp-uniform branch
+            have[u] = live && u0 + u < cnt;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+              xv[u].v[j] = 0.f;
+              ev[u].v[j] = 0.f;
+            }
+            if (have[u]) {
               xv[u] = load_vec<VEC>(g.x_src + static_cast<int64_t>(s) * C + cbase);
               if (g.edge_attr) ev[u] = load_vec<VEC>(g.edge_attr + static_cast<int64_t>(ei) * C + cbase);
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (live && u0 + u < cnt) {
+          for (int j = 0; j < VEC; ++j) {
+            float msg[4];
 #pragma unroll
-              for (int j = 0; j < VEC; ++j) {
-                float v = xv[u].v[j];
-                if (g.edge_attr) v += ev[u].v[j];
-                const float msg = g.raw ? v : fmaxf(v, 0.f) + g.eps;   // torch_vertex.py:85
-                if (kSoftmax) {
-                  const float z = msg * t;
-                  const float d = z - M[j];
-                  const float ex = __expf(-fabsf(d));
-                  if (d > 0.f) {            // new running max: rescale what was accumulated
-                    S[j] = fmaf(S[j], ex, 1.f);
-                    W[j] = fmaf(W[j], ex, msg);
-                    M[j] = z;
+            for (int u = 0; u < 4; ++u) {
+              float v = xv[u].v[j];
+              if (g.edge_attr) v += ev[u].v[j];
+              msg[u] = g.raw ? v : fmaxf(v, 0.f) + g.eps;   // torch_vertex.py:85
+            }
+            if (kSoftmax) {
+              // Four edges per running-max update, branch-free, 5 exp2 per 4 elements:
+              // zl = msg * t * log2(e); newM = max(M, zl0..3); S = S*2^(M-newM) + sum 2^(zl-newM).
+              float zl[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) zl[u] = have[u] ? msg[u] * tl : -INFINITY;
+              const float newM = fmaxf(fmaxf(M[j], fmaxf(zl[0], zl[1])), fmaxf(zl[2], zl[3]));
+              const float sc = fast_exp2(M[j] - newM);          // M = -inf first time: 0
+              const float e0 = fast_exp2(zl[0] - newM), e1 = fast_exp2(zl[1] - newM);
+              const float e2 = fast_exp2(zl[2] - newM), e3 = fast_exp2(zl[3] - newM);
+              S[j] = fmaf(S[j], sc, (e0 + e1) + (e2 + e3));
+              W[j] = fmaf(W[j], sc, fmaf(e0, msg[0], e1 * msg[1]) + fmaf(e2, msg[2], e3 * msg[3]));
+              M[j] = newM;
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (have[u]) {
+                  if (kPower) {
+                    const float uu = fminf(fmaxf(msg[u], 1e-7f), 10.f);  // torch_message.py:69-70
+                    W[j] += __powf(uu, p);
+                  } else if (AGGR == DGCN_AGGR_MAX) {
+                    W[j] = fmaxf(W[j], msg[u]);
                   } else {
-                    S[j] += ex;
-                    W[j] = fmaf(ex, msg, W[j]);
+                    W[j] += msg[u];
                   }
-                } else if (kPower) {
-                  const float uu = fminf(fmaxf(msg, 1e-7f), 10.f);  // torch_message.py:69-70
-                  W[j] += __powf(uu, p);
-                } else if (AGGR == DGCN_AGGR_MAX) {
-                  W[j] = fmaxf(W[j], msg);
-                } else {
-                  W[j] += msg;
                 }
               }
             }
