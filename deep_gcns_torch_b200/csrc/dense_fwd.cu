@@ -37,7 +37,7 @@ size_t knn_workspace_bytes(int64_t B, int64_t C, int64_t N, int64_t K) {
   size_t bytes = align_up(static_cast<size_t>(B) * N * 4, 256);
   if (tc_shape_ok(C, N, K)) {
     const int64_t cpad = (C + 15) / 16 * 16;
-    bytes += align_up(static_cast<size_t>(B) * 3 * cpad * N * 2, 256);   // bf16 planes
+    bytes += align_up(static_cast<size_t>(B) * TC_PLANES * cpad * N * 2, 256);   // bf16 planes
     bytes += align_up(static_cast<size_t>(B) * N * C * 4, 256);          // node-major copy
     bytes += align_up(static_cast<size_t>(B) * 4, 256);                  // per-cloud max |x|^2
     bytes += align_up(static_cast<size_t>(B) * N * 4 + 256, 256);        // fail counter + list
@@ -59,7 +59,7 @@ static int next_pow2(int v) {
 static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const float* xt, int64_t* n_partial) {
   const int B = a.B, N = a.N, C = a.C, K = a.K;
   const int cpad = (C + 15) / 16 * 16;
-  __nv_bfloat16* planes = ws.take<__nv_bfloat16>(static_cast<size_t>(B) * 3 * cpad * N);
+  __nv_bfloat16* planes = ws.take<__nv_bfloat16>(static_cast<size_t>(B) * TC_PLANES * cpad * N);
   float* xt_own = xt ? nullptr : ws.take<float>(static_cast<size_t>(B) * N * C);
   float* sqmax = ws.take<float>(static_cast<size_t>(B));
   int* fail = ws.take<int>(static_cast<size_t>(B) * N + 64);

@@ -128,7 +128,10 @@ constexpr uint32_t kIdescBf16MnMn128x128 =
     (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 // ---- operand split ----------------------------------------------------------------------------
-// planes (B, 3, Cpad, N) bf16: x = hi + mid + lo up to 2^-24 relative; channels >= C are zero.
+// planes (B, TC_PLANES, Cpad, N) bf16: x = hi + mid up to 2^-17 relative (|x - hi - mid| <= 2^-18 |x|);
+// channels >= C are zero.  Four bf16 products hi*hi, hi*mid, mid*hi, mid*mid then reproduce
+// x_i.x_j to ~2^-16 relative - a pre-filter accuracy, the ranking itself is redone in exact fp32.
+constexpr int TC_PLANES = 2;
 __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C, int Cpad, int N,
                                   __nv_bfloat16* __restrict__ planes) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,15 +139,11 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t sb, int64
   if (n >= N) return;
   float v = c < C ? __ldg(x + b * sb + c * sc + n) : 0.f;
   __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  float r1 = v - __bfloat162float(hi);
-  __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-  float r2 = r1 - __bfloat162float(mid);
-  __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+  __nv_bfloat16 mid = __float2bfloat16_rn(v - __bfloat162float(hi));
   const int64_t plane = static_cast<int64_t>(Cpad) * N;
-  __nv_bfloat16* base = planes + (static_cast<int64_t>(b) * 3) * plane + static_cast<int64_t>(c) * N + n;
+  __nv_bfloat16* base = planes + (static_cast<int64_t>(b) * TC_PLANES) * plane + static_cast<int64_t>(c) * N + n;
   base[0] = hi;
   base[plane] = mid;
-  base[2 * plane] = lo;
 }
 
 // sq (B,N) as in sqnorm_kernel plus the per-cloud maximum (for the certification bound)
@@ -177,13 +176,14 @@ struct TcArgs {
 constexpr int TC_THREADS = 256;                       // two warpgroups, each thread r / r+128 owns query r
 constexpr int TC_FLUSH_AT = 9;                        // flush when any lane of the warp buffered this many
 constexpr int TC_BUF = 16;                            // >= TC_FLUSH_AT - 1 + 8 (checked every 8 columns)
-constexpr int TC_STAGE_BYTES = 3 * 2 * TC_MAX_C * 128;   // 48 KB: 3 planes x 2 MN blocks x 64 rows x 128 B
+constexpr int TC_WORK_BYTES = 144 * 1024;              // >= 3 stages; sized for the post-streaming lists + staging
+constexpr int TC_STAGE_BYTES = TC_PLANES * 2 * TC_MAX_C * 128;   // 32 KB: planes x 2 MN blocks x 64 rows x 128 B
 
 struct TcSmem {
   // `work`: operand area while streaming = [queries 48 KB | stage of warpgroup 0 | stage of warpgroup 1],
   // all canonical MN-major SWIZZLE_128B: [plane][mn_block(2)][Cpad rows][128 B].  Afterwards the same
   // 144 KB hold the two per-warpgroup candidate lists (front) and sel / staging buffers (back).
-  unsigned char work[3 * TC_STAGE_BYTES];
+  unsigned char work[TC_WORK_BYTES];
   uint64_t cbuf[TC_BUF * TC_THREADS];               // 32 KB private candidate buffers, slot-major
   float sqj[2][2][TILE];                            // [warpgroup][tile parity][column]
   float cut[2][TILE];                               // approx key of each list's last entry (inf if not full)
@@ -204,7 +204,7 @@ __device__ __forceinline__ void tc_load_tile(unsigned char* dst, const __nv_bflo
   const __nv_bfloat16* src = planes_b + static_cast<int64_t>(row0) * N + p0 + ch * 8;
   unsigned char* d = dst + blk * (Cpad * 128) + row0 * 128 + ((c16 ^ row0) << 4);
   const int groups = Cpad >> 3;
-  for (int pl = 0; pl < 3; ++pl) {
+  for (int pl = 0; pl < TC_PLANES; ++pl) {
     const __nv_bfloat16* sp = src + pl * plane;
     unsigned char* dp = d + pl * (2 * Cpad * 128);
     for (int n = 0; n < groups; ++n) cp_async16(dp + n * 1024, sp + static_cast<int64_t>(n) * 8 * N);
@@ -213,6 +213,9 @@ __device__ __forceinline__ void tc_load_tile(unsigned char* dst, const __nv_bflo
 
 __device__ __forceinline__ void wg_barrier(int wg) {
   asm volatile("bar.sync %0, %1;" ::"r"(1 + wg), "r"(TILE) : "memory");
+}
+__device__ __forceinline__ void gate_barrier() {     // both warpgroups, exactly once per thread
+  asm volatile("bar.sync 6, %0;" ::"r"(2 * TILE) : "memory");
 }
 
 // Branch-free insertion of (nk, nv) into the ascending register-resident list (k, v):
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
   const int b = blockIdx.y, q0 = blockIdx.x * TILE;
   const int N = a.N, Cpad = t.Cpad;
   const int plane_bytes = 2 * Cpad * 128;
-  const __nv_bfloat16* planes_b = t.planes + static_cast<int64_t>(b) * 3 * Cpad * N;
+  const __nv_bfloat16* planes_b = t.planes + static_cast<int64_t>(b) * TC_PLANES * Cpad * N;
   const float* sqb = a.sq + static_cast<int64_t>(b) * N;
   unsigned char* qstage = sm.work;
   unsigned char* mystage = sm.work + (1 + wg) * TC_STAGE_BYTES;
@@ -313,12 +316,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
     if (r == 0) {
       tc_fence_after();
       const uint32_t abase = smem_u32(qstage), bbase = smem_u32(mystage);
-      const int pa[6] = {0, 0, 1, 1, 0, 2};   // hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi
-      const int pb[6] = {0, 1, 0, 1, 2, 0};
+      const int pa[4] = {0, 0, 1, 1};   // hi*hi, hi*mid, mid*hi, mid*mid
+      const int pb[4] = {0, 1, 0, 1};
       uint32_t acc = 0;
       for (int kk = 0; kk < Cpad / 16; ++kk) {
 #pragma unroll
-        for (int term = 0; term < 6; ++term) {
+        for (int term = 0; term < 4; ++term) {
           const uint64_t da = umma_desc_mn_sw128(abase + pa[term] * plane_bytes + kk * 2048, Cpad * 128, 1024);
           const uint64_t db = umma_desc_mn_sw128(bbase + pb[term] * plane_bytes + kk * 2048, Cpad * 128, 1024);
           umma_bf16(tmem, da, db, kIdescBf16MnMn128x128, acc);
@@ -335,6 +338,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
       cp_async_commit();
       sm.sqj[wg][par ^ 1][r] = __ldg(sqb + (tile + 2) * TILE + r);
     }
+    // Only warpgroup 0 pays for filling an empty list: warpgroup 1 holds its first filter until
+    // warpgroup 0 has published a threshold from its first tile.
+    if (wg == 1 && tile == 1) gate_barrier();
     // filter: thread = TMEM lane = query; approx key = |x_j|^2 - 2 x_i.x_j (row-constant |x_i|^2 omitted)
     const int j0 = tile * TILE;
     const float4* sqj4 = reinterpret_cast<const float4*>(sm.sqj[wg][par]);
@@ -388,7 +394,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
         }
       }
     }
+    if (wg == 0 && tile == 0) {   // publish after the first tile and open the gate
+      flush();
+      gate_barrier();
+    }
   }
+  if (wg == 1 && ntiles < 2) gate_barrier();   // arrive once even without a tile
   flush();
   tc_fence_before();
   __syncthreads();   // every MMA has completed, nobody touches operands or TMEM any more
@@ -472,9 +483,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
     if (ok && cut < INFINITY) {
       const float dk = ordered_to_float(static_cast<uint32_t>(kth >> 32));
       const float smax = __ldg(t.sqmax + b);
-      // |approx - exact fp32| <= eps: 6 truncated bf16 products (2^-21 rel. to |x_i||x_j|), ~6*Cpad fp32
-      // tensor-core accumulations and Cpad FMA-chain roundings (2^-23 each), the final additions.
-      const float eps = (2.0f * (4.768e-7f + (7.0f * Cpad + 8.0f) * 1.1921e-7f)) * sqrtf(sqq * smax) +
+      // |approx - exact fp32| <= eps: 4 bf16 products of the (hi, mid) split (2^-15.5 rel. to |x_i||x_j|),
+      // ~4*Cpad fp32 tensor-core accumulations and Cpad FMA-chain roundings (2^-23 each), the final additions.
+      const float eps = (2.0f * (2.158e-5f + (5.0f * Cpad + 8.0f) * 1.1921e-7f)) * sqrtf(sqq * smax) +
                         4.768e-7f * (sqq + smax);
       ok = (dk + eps < cut + sqq);
     }
@@ -486,8 +497,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
   }
   __syncthreads();
   // ---- consumer: sel / staging live at the back of the work area (lists occupy < 78 KB of the front) --------
-  int* sel = reinterpret_cast<int*>(sm.work + 3 * TC_STAGE_BYTES - 66 * 1024);
-  float* stage_max = reinterpret_cast<float*>(sm.work + 3 * TC_STAGE_BYTES - 34 * 1024);
+  int* sel = reinterpret_cast<int*>(sm.work + TC_WORK_BYTES - 66 * 1024);
+  float* stage_max = reinterpret_cast<float*>(sm.work + TC_WORK_BYTES - 34 * 1024);
   float* stage_min = stage_max + 32 * STAGE_LD + 32;
   cta_epilogue<TC_THREADS / 32>(a, b, q0, la, sm.ok, sel, stage_max, stage_min, blockIdx.y * gridDim.x + blockIdx.x);
 }
