@@ -1,5 +1,6 @@
 // Dense path, forward: C ABI entry points dgcn_knn_graph / dgcn_graph_conv_forward /
 // dgcn_dyn_conv_forward and the node-level kernels around the selection kernels.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include "knn_tc.cuh"
@@ -45,6 +46,7 @@ size_t knn_workspace_bytes(int64_t B, int64_t C, int64_t N, int64_t K) {
   if (K > SMALL_K_MAX) {
     const int64_t ldd = (N + 3) / 4 * 4;
     bytes += align_up(knn_slab_clouds(B, N) * N * ldd * 4, 256);
+    bytes += align_up(knn_slab_clouds(B, N) * N * 4 + 256, 256);   // rows the sampled select hands to the exact kernel
   }
   return bytes + 256;
 }
@@ -134,39 +136,57 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
     DGCN_LAUNCH_CHECK();
     return DGCN_OK;
   }
-  if (K <= SMALL_K_MAX) {
-    const size_t smem = sizeof(SmallSmem<2>);
-    DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-    {
-      KernelTimer timer(stream, "knn");
-      knn_small_kernel<2><<<grid, NTHREADS, smem, stream>>>(a);
-    }
-    DGCN_LAUNCH_CHECK();
-    return DGCN_OK;
-  }
   if (K > LARGE_K_MAX) return DGCN_ERR_UNSUPPORTED;
   const int ldd = (N + 3) / 4 * 4;
   const int nbmax = static_cast<int>(knn_slab_clouds(B, N));
   float* drows = ws.take<float>(static_cast<size_t>(nbmax) * N * ldd);
   if (!ws.ok) return DGCN_ERR_WORKSPACE;
   const int KP = next_pow2(K);
-  const size_t per_warp = static_cast<size_t>(KP) * 8 + static_cast<size_t>(N) * 4 + static_cast<size_t>((a.k + 31) / 32 * 32) * 4;
+  const size_t per_warp = static_cast<size_t>(KP) * 8 + static_cast<size_t>(ldd) * 4 + static_cast<size_t>((a.k + 31) / 32 * 32) * 4;   // ldd = N rounded up to 4 keeps every warp's u64 array 16-byte aligned
   int warps = static_cast<int>((200u << 10) / per_warp);
   if (warps < 1) return DGCN_ERR_UNSUPPORTED;   // a single row does not fit in shared memory
   if (warps > 4) warps = 4;
   const size_t smem = per_warp * warps;
   DGCN_CUDA_TRY(cudaFuncSetAttribute(select_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
+  // sampled fast select: bound = sample_rank-th of 128 samples (mean + 2.5 sigma + 2 of the K/N quantile)
+  const double pq = static_cast<double>(K) / N;
+  int sample_rank = static_cast<int>(128.0 * pq + 2.5 * sqrt(128.0 * pq * (1.0 - pq)) + 2.0) + 1;
+  if (sample_rank > 127) sample_rank = 127;
+  const int64_t expect = static_cast<int64_t>(1.35 * (sample_rank + 1) / 128.0 * N) + 32;
+  int cap = next_pow2(static_cast<int>(expect > 2 * K ? expect : 2 * K));
+  if (cap > 2048) cap = 2048;
+  const bool fast = N >= 512 && cap >= K;
+  const size_t per_warp_f = static_cast<size_t>(cap) * 8 + static_cast<size_t>((a.k + 31) / 32 * 32) * 4;
+  int warps_f = static_cast<int>((100u << 10) / per_warp_f);
+  if (warps_f > 8) warps_f = 8;
+  if (warps_f < 1) warps_f = 1;
+  const size_t smem_f = per_warp_f * warps_f;
+  int* rowlist = nullptr;
+  if (fast) {
+    rowlist = ws.take<int>(static_cast<size_t>(nbmax) * N + 64);
+    if (!ws.ok) return DGCN_ERR_WORKSPACE;
+    DGCN_CUDA_TRY(cudaFuncSetAttribute(select_rows_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem_f)));
+  }
   KernelTimer timer(stream, "knn");
   for (int b0 = 0; b0 < B; b0 += nbmax) {
     const int nb = (B - b0 < nbmax) ? (B - b0) : nbmax;
     dist_rows_kernel<<<dim3(ceil_div(N, TILE), ceil_div(N, TILE), nb), NTHREADS, 0, stream>>>(a, b0, drows, ldd);
     DGCN_LAUNCH_CHECK();
     const int64_t rows = static_cast<int64_t>(nb) * N;
-    select_rows_kernel<<<static_cast<unsigned>(ceil_div(rows, warps)), warps * 32, smem, stream>>>(
-        a, b0, nb, drows, ldd, KP, N, warps);
-    DGCN_LAUNCH_CHECK();
+    if (fast) {
+      DGCN_CUDA_TRY(cudaMemsetAsync(rowlist, 0, 256, stream));
+      select_rows_fast_kernel<<<static_cast<unsigned>(ceil_div(rows, warps_f)), warps_f * 32, smem_f, stream>>>(
+          a, b0, nb, drows, ldd, cap, sample_rank, warps_f, rowlist, rowlist + 64);
+      DGCN_LAUNCH_CHECK();
+      select_rows_kernel<<<296, warps * 32, smem, stream>>>(a, b0, nb, drows, ldd, KP, ldd, warps, rowlist + 64, rowlist);
+      DGCN_LAUNCH_CHECK();
+    } else {
+      select_rows_kernel<<<static_cast<unsigned>(ceil_div(rows, warps)), warps * 32, smem, stream>>>(
+          a, b0, nb, drows, ldd, KP, ldd, warps, nullptr, nullptr);
+      DGCN_LAUNCH_CHECK();
+    }
   }
   return DGCN_OK;
 }

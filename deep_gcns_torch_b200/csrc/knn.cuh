@@ -1,11 +1,11 @@
 // Dilated kNN selection kernels (D1/D2 of SURVEY.md 2b) with the fused
 // gather/max consumers (D3/D4) as epilogues.
 //
-//   small path  (K = k*dilation <= 64): one CTA owns 128 queries of a cloud and
+//   small path  (K = k*dilation <= 32): one CTA owns 128 queries of a cloud and
 //     streams all candidates through 128x128 fp32 distance tiles; a register
 //     level threshold test feeds per-query candidate buffers in shared memory,
 //     which warps merge into per-query sorted lists.  No (N,N) matrix exists.
-//   large path  (K > 64): distance rows of an L2-sized slab of clouds are
+//   large path  (K > 32): distance rows of an L2-sized slab of clouds are
 //     written to the workspace, then one warp per row does an exact
 //     bit-bisection select (in-place compaction in shared memory) of the K-th
 //     key, gathers the K winners in index order and bitonic-sorts them.
@@ -18,7 +18,7 @@
 namespace dgcn {
 
 constexpr int MAX_KEEP = 128;       // k (kept neighbours) supported with explicit column lists
-constexpr int SMALL_K_MAX = 64;     // K handled by the fused small path
+constexpr int SMALL_K_MAX = 32;     // K handled by the fused fp32 small path (above: slab path)
 constexpr int LARGE_K_MAX = 2048;   // K handled by the slab path
 
 enum EpiMode { EPI_INDEX = 0, EPI_EDGE = 1, EPI_MR = 2 };
@@ -424,10 +424,61 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t* s, int n, int lane) 
   }
 }
 
+// Per-row consumer shared by the slab kernels: sk holds the row's sorted keys (ascending), sel is a
+// k-entry scratch.  Writes the selected neighbour ids and runs the fused EdgeConv / MRConv consumer.
+__device__ __forceinline__ void row_consume(const KnnArgs& a, int b, int q, const uint64_t* sk, int* sel, int lane) {
+  const int N = a.N, k = a.k;
+  const Epilogue& e = a.epi;
+  const int64_t node0 = static_cast<int64_t>(b) * N;
+  for (int l = lane; l < k; l += 32) {
+    int idx = static_cast<int>(static_cast<uint32_t>(sk[keep_rank(a, l)]));
+    sel[l] = idx;
+    int64_t o = (node0 + q) * k + l;
+    if (e.nbr) e.nbr[o] = idx;
+    if (e.edge_index) {
+      e.edge_index[o] = idx;
+      e.edge_index[static_cast<int64_t>(a.B) * N * k + o] = q;
+    }
+  }
+  __syncwarp();
+  if (e.mode == EPI_INDEX) return;
+  if (e.mode == EPI_EDGE) {
+    const float slope = epi_slope(e);
+    const bool train = e.norm == DGCN_NORM_BATCH_TRAIN;
+    for (int c0 = 0; c0 < e.c_out; c0 += 32) {
+      const int c = c0 + lane;
+      float vmax, vmin, s1 = 0.f, s2 = 0.f, bs, bt;
+      bn_affine(e, c, bs, bt);
+      edge_query(e, node0, q, sel, k, c, slope, vmax, vmin, s1, s2);
+      if (c < e.c_out) {
+        int64_t o = (static_cast<int64_t>(b) * e.c_out + c) * N + q;
+        if (train) {
+          e.out[o] = vmax;
+          e.out_min[o] = vmin;
+          // one partial slot per query row: [row][2][c_out]
+          e.partial[(static_cast<int64_t>(node0 + q) * 2 + 0) * e.c_out + c] = s1;
+          e.partial[(static_cast<int64_t>(node0 + q) * 2 + 1) * e.c_out + c] = s2;
+        } else {
+          e.out[o] = bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt);
+        }
+      }
+    }
+  } else {
+    for (int c0 = 0; c0 < e.c_in; c0 += 32) {
+      const int c = c0 + lane;
+      float r = mr_query(e, node0, q, sel, k, c);
+      if (c < e.c_in) e.r_out[(static_cast<int64_t>(b) * e.c_in + c) * N + q] = r;
+    }
+  }
+}
+
 // One warp per query row: exact K smallest (key = ordered distance, index), sorted.
 // dynamic smem per warp: keys[nkeys] (u32) | sk[KP] (u64) | sel[k] (int)
+// With row_list != null the kernel instead completes the rows listed there (rows the sampled fast
+// kernel could not bound), grid-striding over *row_count entries.
 __global__ void select_rows_kernel(const KnnArgs a, int b0, int nb, const float* __restrict__ drows,
-                                   int ldd, int KP, int nkeys, int warps_per_cta) {
+                                   int ldd, int KP, int nkeys, int warps_per_cta, const int* __restrict__ row_list,
+                                   const int* __restrict__ row_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = a.N, K = a.K, k = a.k;
@@ -437,8 +488,10 @@ __global__ void select_rows_kernel(const KnnArgs a, int b0, int nb, const float*
   uint32_t* keys = reinterpret_cast<uint32_t*>(mine + static_cast<size_t>(KP) * 8);
   int* sel = reinterpret_cast<int*>(mine + static_cast<size_t>(KP) * 8 + static_cast<size_t>(nkeys) * 4);
 
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * warps_per_cta + warp;
-  if (row >= static_cast<int64_t>(nb) * N) return;   // whole warp exits together
+  const int64_t total_rows = row_list ? static_cast<int64_t>(*row_count) : static_cast<int64_t>(nb) * N;
+  for (int64_t it = static_cast<int64_t>(blockIdx.x) * warps_per_cta + warp; it < total_rows;
+       it += static_cast<int64_t>(gridDim.x) * warps_per_cta) {
+  const int64_t row = row_list ? row_list[it] : it;
   const int b = b0 + static_cast<int>(row / N), q = static_cast<int>(row % N);
   const float* drow = drows + row * ldd;
 
@@ -516,48 +569,97 @@ __global__ void select_rows_kernel(const KnnArgs a, int b0, int nb, const float*
   __syncwarp();
   // 4. sort, 5. consume
   warp_bitonic_sort(sk, KP, lane);
-  const Epilogue& e = a.epi;
-  const int64_t node0 = static_cast<int64_t>(b) * N;
-  for (int l = lane; l < k; l += 32) {
-    int idx = static_cast<int>(static_cast<uint32_t>(sk[keep_rank(a, l)]));
-    sel[l] = idx;
-    int64_t o = (node0 + q) * k + l;
-    if (e.nbr) e.nbr[o] = idx;
-    if (e.edge_index) {
-      e.edge_index[o] = idx;
-      e.edge_index[static_cast<int64_t>(a.B) * N * k + o] = q;
-    }
+  row_consume(a, b, q, sk, sel, lane);
+  __syncwarp();
+  }
+}
+
+// Fast variant: a 128-key sample of the row bounds the K-th distance from above, one pass compacts
+// every key below that bound (in index order) into shared memory, a bitonic sort of the next power of
+// two finishes.  Exact whenever the compacted set holds >= K and <= CAP keys; other rows go to a list
+// that select_rows_kernel completes.  dynamic smem per warp: sk[CAP] (u64) | sel[k] (int).
+__global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const float* __restrict__ drows, int ldd,
+                                        int CAP, int sample_rank, int warps_per_cta, int* __restrict__ row_count,
+                                        int* __restrict__ row_list) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = a.N, K = a.K, k = a.k;
+  const size_t per_warp = static_cast<size_t>(CAP) * 8 + static_cast<size_t>((k + 31) / 32 * 32) * 4;
+  unsigned char* mine = smem_raw + per_warp * warp;
+  uint64_t* sk = reinterpret_cast<uint64_t*>(mine);
+  int* sel = reinterpret_cast<int*>(mine + static_cast<size_t>(CAP) * 8);
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * warps_per_cta + warp;
+  if (row >= static_cast<int64_t>(nb) * N) return;   // whole warp exits together
+  const int b = b0 + static_cast<int>(row / N), q = static_cast<int>(row % N);
+  const float* drow = drows + row * ldd;
+  // 1. sample 128 keys spread over the row, sort them, take the sample_rank-th as the bound
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int s = lane + 32 * u;
+    const int i = static_cast<int>((static_cast<int64_t>(s) * N) >> 7);
+    uint32_t key = float_to_ordered(__ldg(drow + i));
+    if (a.exclude_self && i == q) key = 0xFFFFFFFFu;
+    sk[s] = static_cast<uint64_t>(key);
   }
   __syncwarp();
-  if (e.mode == EPI_INDEX) return;
-  if (e.mode == EPI_EDGE) {
-    const float slope = epi_slope(e);
-    const bool train = e.norm == DGCN_NORM_BATCH_TRAIN;
-    for (int c0 = 0; c0 < e.c_out; c0 += 32) {
-      const int c = c0 + lane;
-      float vmax, vmin, s1 = 0.f, s2 = 0.f, bs, bt;
-      bn_affine(e, c, bs, bt);
-      edge_query(e, node0, q, sel, k, c, slope, vmax, vmin, s1, s2);
-      if (c < e.c_out) {
-        int64_t o = (static_cast<int64_t>(b) * e.c_out + c) * N + q;
-        if (train) {
-          e.out[o] = vmax;
-          e.out_min[o] = vmin;
-          // one partial slot per query row: [row][2][c_out]
-          e.partial[(static_cast<int64_t>(node0 + q) * 2 + 0) * e.c_out + c] = s1;
-          e.partial[(static_cast<int64_t>(node0 + q) * 2 + 1) * e.c_out + c] = s2;
-        } else {
-          e.out[o] = bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt);
-        }
+  warp_bitonic_sort(sk, 128, lane);
+  // keep the sorted sample in registers: lane l holds samples l, l+32, l+64, l+96
+  uint32_t smp[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) smp[u] = static_cast<uint32_t>(sk[lane + 32 * u]);
+  __syncwarp();
+  // 2. compaction in index order of every key <= bound; if the sample misjudged the row (too few or too
+  //    many keys below the bound) move the bound along the sorted sample and try again
+  int w = 0, rank = sample_rank, lo_rank = -1, hi_rank = 128;   // lo_rank: too few, hi_rank: too many
+  bool ok = false;
+  for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
+    uint32_t bound = __shfl_sync(0xffffffffu, smp[0], rank & 31);
+    if ((rank >> 5) == 1) bound = __shfl_sync(0xffffffffu, smp[1], rank & 31);
+    if ((rank >> 5) == 2) bound = __shfl_sync(0xffffffffu, smp[2], rank & 31);
+    if ((rank >> 5) == 3) bound = __shfl_sync(0xffffffffu, smp[3], rank & 31);
+    w = 0;
+    for (int i0 = 0; i0 < N; i0 += 128) {
+      uint32_t key[4];
+      bool take[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        key[u] = 0xFFFFFFFFu;
+        if (i < N) key[u] = float_to_ordered(__ldg(drow + i));
+        take[u] = (i < N) && key[u] <= bound && !(a.exclude_self && i == q);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned m = __ballot_sync(0xffffffffu, take[u]);
+        const int pos = w + __popc(m & ((1u << lane) - 1u));
+        if (take[u] && pos < CAP) sk[pos] = (static_cast<uint64_t>(key[u]) << 32) | static_cast<uint32_t>(i0 + u * 32 + lane);
+        w += __popc(m);
       }
     }
-  } else {
-    for (int c0 = 0; c0 < e.c_in; c0 += 32) {
-      const int c = c0 + lane;
-      float r = mr_query(e, node0, q, sel, k, c);
-      if (c < e.c_in) e.r_out[(static_cast<int64_t>(b) * e.c_in + c) * N + q] = r;
+    if (w < K) {
+      lo_rank = rank;
+      rank = min(127, max(rank + 1, (rank * 3) / 2 + 1));
+      if (rank >= hi_rank) rank = hi_rank - 1;
+      if (rank <= lo_rank) break;          // bracket closed (massive ties): exact kernel
+    } else if (w > CAP) {
+      hi_rank = rank;
+      rank = (lo_rank + rank) / 2;
+      if (rank <= lo_rank) break;
+    } else {
+      ok = true;
     }
+    __syncwarp();
   }
+  if (!ok) {   // leave the row to the exact bisection kernel
+    if (lane == 0) row_list[atomicAdd(row_count, 1)] = static_cast<int>(row);
+    return;
+  }
+  int KP = 128;
+  while (KP < w) KP <<= 1;
+  for (int i = w + lane; i < KP; i += 32) sk[i] = KEY_MAX;
+  __syncwarp();
+  warp_bitonic_sort(sk, KP, lane);
+  row_consume(a, b, q, sk, sel, lane);
 }
 
 }  // namespace dgcn
