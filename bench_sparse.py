@@ -19,6 +19,8 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--products", action="store_true")
+    ap.add_argument("--zipf", action="store_true", help="power-law in-degrees (hub rows)")
+    ap.add_argument("--no-hubs", action="store_true", help="disable the CTA-per-hub-row kernel")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--aggr", default="softmax_sg")
     ap.add_argument("--cpu", action="store_true", help="also time the oracle port on the host")
@@ -36,11 +38,16 @@ def main():
         N = 169343
         s, d = torch.randint(0, N, (1166243,), generator=g), torch.randint(0, N, (1166243,), generator=g)
         ei = osp.to_undirected_with_self_loops(s, d, N)
+    if a.zipf:
+        u = torch.rand(ei.shape[1], generator=g).clamp_min(1e-9)
+        ei[1] = (u.pow(-2.0) - 1).clamp(max=N - 1).long()
     E = ei.shape[1]
     x = torch.randn(N, C, generator=g).to(dev)
     eic = ei.to(dev)
     t0 = time.perf_counter()
     csr = _native.csr_build(eic, N)
+    if a.no_hubs:
+        csr = csr[:3]
     torch.cuda.synchronize()
     csr_ms = (time.perf_counter() - t0) * 1e3
     conv = S.GENConv(C, C, aggr=a.aggr, t=0.1, mlp_layers=1).to(dev).eval()

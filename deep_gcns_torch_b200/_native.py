@@ -36,6 +36,15 @@ class DilationC(ctypes.Structure):
     _fields_ = [("k", c_i64), ("dilation", c_i64), ("cols_host", ctypes.POINTER(c_i32))]
 
 
+class CsrHubsC(ctypes.Structure):
+    _fields_ = [("items", ctypes.c_void_p), ("rows", ctypes.c_void_p), ("counts", ctypes.c_void_p),
+                ("min_degree", c_i32), ("seg_edges", c_i32), ("partial", ctypes.c_void_p)]
+
+
+HUB_MIN_DEGREE = 1024      # rows at least this long are aggregated by CTAs instead of one warp
+HUB_SEG_EDGES = 4096       # ... one CTA per segment of this many edges
+
+
 class GenconvParamsC(ctypes.Structure):
     _fields_ = [("aggr", c_i32), ("t", ctypes.c_float), ("t_dev", c_f32p), ("p", ctypes.c_float),
                 ("p_dev", c_f32p), ("y", ctypes.c_float), ("y_dev", c_f32p), ("eps", ctypes.c_float),
@@ -80,7 +89,9 @@ def _declare(lib):
     lib.dgcn_csr_build.argtypes = [vp, c_i64, c_i64, vp, vp, vp, vp, sz, vp]
     lib.dgcn_genconv_aggregate.restype = ctypes.c_int
     lib.dgcn_genconv_aggregate.argtypes = [vp, vp, c_i64, c_i64, vp, vp, vp, vp, ctypes.POINTER(GenconvParamsC),
-                                           vp, vp]
+                                           ctypes.POINTER(CsrHubsC), vp, vp]
+    lib.dgcn_csr_hub_rows.restype = ctypes.c_int
+    lib.dgcn_csr_hub_rows.argtypes = [vp, c_i64, c_i64, c_i32, c_i32, vp, vp, vp, vp]
     lib.dgcn_genconv_aggregate_backward.restype = ctypes.c_int
     lib.dgcn_genconv_aggregate_backward.argtypes = [vp, vp, c_i64, c_i64, c_i64, vp, vp, vp, vp,
                                                     ctypes.POINTER(GenconvParamsC), c_i32, vp, vp, vp, vp, vp, vp]
@@ -329,9 +340,21 @@ def csr_build(edge_index, num_nodes):
         rc = l.dgcn_csr_build(_ptr(edge_index), E, num_nodes, _ptr(rowptr), _ptr(src), _ptr(eid), _ptr(ws),
                               ws.numel(), _stream(dev))
         _check(rc, "dgcn_csr_build")
-    if E == 0:          # keep the 1-element placeholders: a 0-element tensor has a null data_ptr
-        return rowptr, src, eid
-    return rowptr, src, eid
+        # long rows (hubs of power-law graphs): (row, segment) work items, listed once, on the device
+        hubs = None
+        if E >= HUB_MIN_DEGREE:
+            max_items = E // HUB_SEG_EDGES + E // HUB_MIN_DEGREE + 2
+            max_rows = E // HUB_MIN_DEGREE + 2
+            items = torch.empty(2 * max_items, dtype=torch.int32, device=dev)
+            rows = torch.empty(3 * max_rows, dtype=torch.int32, device=dev)
+            counts = torch.zeros(2, dtype=torch.int32, device=dev)
+            _check(l.dgcn_csr_hub_rows(_ptr(rowptr), num_nodes, E, HUB_MIN_DEGREE, HUB_SEG_EDGES, _ptr(items),
+                                       _ptr(rows), _ptr(counts), _stream(dev)), "dgcn_csr_hub_rows")
+            n_items = int(counts[0])            # one-time host read at graph-build time
+            if n_items > 0:
+                hubs = (items, rows, counts, n_items)
+    # (src / eid keep >= 1 element: a 0-element tensor has a null data_ptr)
+    return rowptr, src, eid, hubs
 
 
 def _scalar(prm, name, value):
@@ -362,15 +385,21 @@ def genconv_params(aggr, t=1.0, p=1.0, y=0.0, eps=1e-7, msg_scale=None, add_resi
 
 def genconv_aggregate(x_src, x_dst, csr, prm, edge_attr=None):
     """dgcn_genconv_aggregate: out (N, C) = x_dst + MsgNorm(aggregate(message))."""
-    rowptr, src, eid = csr
+    rowptr, src, eid = csr[:3]
     _require_cuda(x_src, x_dst, rowptr, src, eid, edge_attr)
     x_src, x_dst, edge_attr = _f32(x_src), _f32(x_dst), _f32(edge_attr)
     N, C = rowptr.numel() - 1, x_src.shape[1]
     dev = x_src.device
+    hubs = None
     with torch.cuda.device(dev):
+        if len(csr) > 3 and csr[3] is not None:
+            items, rows, counts, n_items = csr[3]
+            partial = torch.empty(n_items * 3 * C, dtype=torch.float32, device=dev)
+            hubs = CsrHubsC(_ptr(items), _ptr(rows), _ptr(counts), HUB_MIN_DEGREE, HUB_SEG_EDGES, _ptr(partial))
         out = torch.empty((N, C), dtype=torch.float32, device=dev)
         rc = lib().dgcn_genconv_aggregate(_ptr(x_src), _ptr(x_dst), N, C, _ptr(rowptr), _ptr(src), _ptr(eid),
-                                          _ptr(edge_attr), ctypes.byref(prm), _ptr(out), _stream(dev))
+                                          _ptr(edge_attr), ctypes.byref(prm),
+                                          ctypes.byref(hubs) if hubs is not None else None, _ptr(out), _stream(dev))
         _check(rc, "dgcn_genconv_aggregate")
     return out
 
@@ -379,7 +408,7 @@ def genconv_aggregate_backward(x_src, x_dst, csr, prm, grad_out, edge_attr=None,
                                need_edge_attr=False):
     """dgcn_genconv_aggregate_backward: (grad_x_src (N_src,C), grad_x_dst (N,C) | None,
     grad_edge_attr | None, grad_scalars (4) = d/dt, d/dp, d/dy, d/dmsg_scale)."""
-    rowptr, src, eid = csr
+    rowptr, src, eid = csr[:3]
     _require_cuda(x_src, x_dst, grad_out, edge_attr)
     x_src, x_dst, edge_attr, grad_out = _f32(x_src), _f32(x_dst), _f32(edge_attr), _f32(grad_out)
     N, C = rowptr.numel() - 1, x_src.shape[1]

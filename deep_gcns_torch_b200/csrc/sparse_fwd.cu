@@ -16,6 +16,9 @@ struct AggrArgs {
   float t; const float* t_dev; float p; const float* p_dev; float y; const float* y_dev;
   float eps; int msg_norm; float msg_scale; const float* msg_scale_dev; int add_residual; int raw;
   float* out;
+  // long rows (hubs): items = (row, segment) pairs, rows = (row, first item, #segments) triples
+  const int32_t* hub_items; const int32_t* hub_item_count; const int32_t* hub_rows; const int32_t* hub_row_count;
+  int hub_min_degree, hub_seg_edges; float* hub_partial;   // [item][3][C] merged (max, sum, weighted sum) states
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -43,14 +46,35 @@ __device__ __forceinline__ VecF<VEC> load_vec(const float* p) {
 template <int VEC>
 __device__ __forceinline__ int chan_of(int lane, int blk, int j) { return blk * 32 * VEC + lane * VEC + j; }
 
-template <int VEC, int NBLK, int AGGR>
+// MODE 0: one warp per destination row (rows of degree >= hub_min_degree are left out when a hub list is
+//         given).
+// MODE 1: one CTA per (hub row, segment of hub_seg_edges edges): its 8 warps take the segment's 32-edge
+//         chunks round robin, their running (max, sum, weighted sum) states are merged in a fixed order and
+//         written to hub_partial.
+// MODE 2: one warp per hub row: merges the row's segment states in segment order, then finishes the row
+//         like MODE 0.  A power-law graph's hubs therefore neither serialise on one warp nor make the
+//         result depend on scheduling.
+template <int VEC, int NBLK, int AGGR, int MODE>
 __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= g.N) return;
+  constexpr bool HUB = MODE == 1;
+  __shared__ float hub_red[HUB ? 8 : 1][3][VEC][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_work = MODE == 1 ? __ldg(g.hub_item_count) : (MODE == 2 ? __ldg(g.hub_row_count) : 0);
+  const int work0 = MODE == 2 ? static_cast<int>(blockIdx.x * 8 + warp) : static_cast<int>(blockIdx.x);
+  const int work_step = MODE == 2 ? static_cast<int>(gridDim.x * 8) : static_cast<int>(gridDim.x);
+  for (int hub_it = work0; MODE != 0 ? hub_it < n_work : hub_it == work0; hub_it += work_step) {
+  int row, seg = 0, item0 = 0, nseg = 0;
+  if (MODE == 0) row = static_cast<int>(blockIdx.x * (blockDim.x >> 5) + warp);
+  else if (MODE == 1) { row = __ldg(g.hub_items + 2 * hub_it); seg = __ldg(g.hub_items + 2 * hub_it + 1); }
+  else { row = __ldg(g.hub_rows + 3 * hub_it); item0 = __ldg(g.hub_rows + 3 * hub_it + 1); nseg = __ldg(g.hub_rows + 3 * hub_it + 2); }
+  if (MODE == 0 && row >= g.N) return;
   const int C = g.C;
-  const int beg = __ldg(g.rowptr + row), end = __ldg(g.rowptr + row + 1);
-  const int deg = end - beg;
+  const int rbeg = __ldg(g.rowptr + row), rend = __ldg(g.rowptr + row + 1);
+  const int deg = rend - rbeg;
+  if (MODE == 0 && g.hub_rows != nullptr && deg >= g.hub_min_degree) return;   // the hub kernels own this row
+  const int beg = MODE == 1 ? rbeg + seg * g.hub_seg_edges : rbeg;
+  const int end = MODE == 1 ? min(rend, beg + g.hub_seg_edges) : (MODE == 2 ? rbeg : rend);   // MODE 2 reads no edges
+  const int e_first = HUB ? beg + 32 * warp : beg, e_step = HUB ? 256 : 32;
   const float t = g.t_dev ? __ldg(g.t_dev) : g.t;
   const float p = g.p_dev ? __ldg(g.p_dev) : g.p;
   const float tl = t * 1.4426950408889634f;   // softmax in base 2
@@ -70,7 +94,7 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
       W[j] = (AGGR == DGCN_AGGR_MAX) ? -INFINITY : 0.f;
     }
     if (blk * 32 * VEC < C) {   // warp-uniform: this channel block exists
-      for (int e0 = beg; e0 < end; e0 += 32) {
+      for (int e0 = e_first; e0 < end; e0 += e_step) {
         const int cnt = min(32, end - e0);
         int my_src = 0, my_eid = 0;
         if (lane < cnt) {
@@ -137,6 +161,65 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
         }
       }
     }
+    if (MODE == 1) {   // merge the 8 warps' states (warp order fixed -> deterministic), publish the segment state
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        hub_red[warp][0][j][lane] = M[j];
+        hub_red[warp][1][j][lane] = S[j];
+        hub_red[warp][2][j][lane] = W[j];
+      }
+      __syncthreads();
+      if (warp == 0 && live) {
+        float* part = g.hub_partial + static_cast<int64_t>(hub_it) * 3 * C;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float Mx = hub_red[0][0][j][lane];
+          for (int w = 1; w < 8; ++w) Mx = fmaxf(Mx, hub_red[w][0][j][lane]);
+          float Ss = 0.f, Ws = (AGGR == DGCN_AGGR_MAX) ? -INFINITY : 0.f;
+          for (int w = 0; w < 8; ++w) {
+            const float Mw = hub_red[w][0][j][lane], Sw = hub_red[w][1][j][lane], Ww = hub_red[w][2][j][lane];
+            if (kSoftmax) {
+              const float sc = Mw == -INFINITY ? 0.f : fast_exp2(Mw - Mx);
+              Ss = fmaf(Sw, sc, Ss);
+              Ws = fmaf(Ww, sc, Ws);
+            } else if (AGGR == DGCN_AGGR_MAX) {
+              Ws = fmaxf(Ws, Ww);
+            } else {
+              Ws += Ww;
+            }
+          }
+          part[cbase + j] = Mx;
+          part[C + cbase + j] = Ss;
+          part[2 * C + cbase + j] = Ws;
+        }
+      }
+      __syncthreads();
+      continue;   // next channel block; the row is finished by MODE 2
+    }
+    if (MODE == 2 && live) {   // merge the row's segment states in segment order
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float Mx = -INFINITY;
+        for (int sg = 0; sg < nseg; ++sg) Mx = fmaxf(Mx, g.hub_partial[static_cast<int64_t>(item0 + sg) * 3 * C + cbase + j]);
+        float Ss = 0.f, Ws = (AGGR == DGCN_AGGR_MAX) ? -INFINITY : 0.f;
+        for (int sg = 0; sg < nseg; ++sg) {
+          const float* part = g.hub_partial + static_cast<int64_t>(item0 + sg) * 3 * C;
+          const float Mw = part[cbase + j], Sw = part[C + cbase + j], Ww = part[2 * C + cbase + j];
+          if (kSoftmax) {
+            const float sc = Mw == -INFINITY ? 0.f : fast_exp2(Mw - Mx);
+            Ss = fmaf(Sw, sc, Ss);
+            Ws = fmaf(Ww, sc, Ws);
+          } else if (AGGR == DGCN_AGGR_MAX) {
+            Ws = fmaxf(Ws, Ww);
+          } else {
+            Ws += Ww;
+          }
+        }
+        M[j] = Mx;
+        S[j] = Ss;
+        W[j] = Ws;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       float r;
@@ -165,6 +248,7 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
 #pragma unroll
       for (int j = 0; j < VEC; ++j) m[blk][j] *= f;
   }
+  if (MODE == 1) continue;   // segments only publish their state
   // MsgNorm (torch_message.py:95-99) + residual (torch_vertex.py:73)
   float xr[NBLK][VEC];
   float n2m = 0.f, n2x = 0.f;
@@ -207,6 +291,7 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
       }
     }
   }
+  }   // hub_it
 }
 
 template <int VEC, int NBLK>
@@ -215,7 +300,11 @@ static int launch_aggr(const AggrArgs& g, cudaStream_t stream) {
   const unsigned grid = static_cast<unsigned>(ceil_div(g.N, warps));
 #define DGCN_AGGR_CASE(A)                                                                   \
   case A:                                                                                   \
-    genconv_aggregate_kernel<VEC, NBLK, A><<<grid, warps * 32, 0, stream>>>(g);             \
+    genconv_aggregate_kernel<VEC, NBLK, A, 0><<<grid, warps * 32, 0, stream>>>(g);          \
+    if (g.hub_rows) {                                                                       \
+      genconv_aggregate_kernel<VEC, NBLK, A, 1><<<592, 256, 0, stream>>>(g);                \
+      genconv_aggregate_kernel<VEC, NBLK, A, 2><<<32, 256, 0, stream>>>(g);                 \
+    }                                                                                       \
     break;
   KernelTimer timer(stream, "aggregate");
   switch (g.aggr) {
@@ -254,9 +343,43 @@ using namespace dgcn;
 
 extern "C" {
 
+// Work list of the long rows: per row ceil(deg / seg_edges) (row, segment) items and one
+// (row, first item, #segments) triple.  Order is arbitrary; every entry is processed independently.
+__global__ void hub_rows_kernel(const int32_t* __restrict__ rowptr, int N, int min_degree, int seg_edges,
+                                int32_t* __restrict__ items, int32_t* __restrict__ item_count,
+                                int32_t* __restrict__ rows, int32_t* __restrict__ row_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int deg = rowptr[i + 1] - rowptr[i];
+  if (deg < min_degree) return;
+  const int nseg = (deg + seg_edges - 1) / seg_edges;
+  const int base = atomicAdd(item_count, nseg);
+  for (int s = 0; s < nseg; ++s) {
+    items[2 * (base + s)] = i;
+    items[2 * (base + s) + 1] = s;
+  }
+  const int r = atomicAdd(row_count, 1);
+  rows[3 * r] = i;
+  rows[3 * r + 1] = base;
+  rows[3 * r + 2] = nseg;
+}
+
+extern "C" int dgcn_csr_hub_rows(const int32_t* rowptr, int64_t N, int64_t E, int32_t min_degree, int32_t seg_edges,
+                                 int32_t* items, int32_t* rows, int32_t* counts, dgcn_stream_t stream) {
+  if (!rowptr || !items || !rows || !counts || N <= 0 || min_degree <= 0 || seg_edges <= 0) return DGCN_ERR_BAD_ARG;
+  (void)E;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DGCN_CUDA_TRY(cudaMemsetAsync(counts, 0, 8, s));
+  hub_rows_kernel<<<static_cast<unsigned>(ceil_div(N, 256)), 256, 0, s>>>(rowptr, static_cast<int>(N), min_degree,
+                                                                         seg_edges, items, counts, rows, counts + 1);
+  DGCN_LAUNCH_CHECK();
+  return DGCN_OK;
+}
+
 int dgcn_genconv_aggregate(const float* x_src, const float* x_dst, int64_t N, int64_t C, const int32_t* rowptr,
                            const int32_t* src, const int32_t* eid, const float* edge_attr,
-                           const dgcn_genconv_params* prm, float* out, dgcn_stream_t stream) {
+                           const dgcn_genconv_params* prm, const dgcn_csr_hubs* hubs, float* out,
+                           dgcn_stream_t stream) {
   if (!x_src || !rowptr || !src || !prm || !out || N < 0 || C <= 0) return DGCN_ERR_BAD_ARG;
   if (!x_dst && (prm->msg_norm || prm->add_residual)) return DGCN_ERR_BAD_ARG;
   if (edge_attr && !eid) return DGCN_ERR_BAD_ARG;
@@ -271,6 +394,12 @@ int dgcn_genconv_aggregate(const float* x_src, const float* x_dst, int64_t N, in
   g.add_residual = prm->add_residual;
   g.raw = prm->raw_message;
   g.out = out;
+  if (hubs && hubs->rows && hubs->items && hubs->counts && hubs->partial && hubs->min_degree > 0 &&
+      hubs->seg_edges > 0) {
+    g.hub_items = hubs->items; g.hub_item_count = hubs->counts; g.hub_rows = hubs->rows;
+    g.hub_row_count = hubs->counts + 1; g.hub_min_degree = hubs->min_degree; g.hub_seg_edges = hubs->seg_edges;
+    g.hub_partial = hubs->partial;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool aligned = ((reinterpret_cast<uintptr_t>(x_src) | reinterpret_cast<uintptr_t>(x_dst) |
                          reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(edge_attr)) & 15) == 0;

@@ -199,9 +199,28 @@ typedef struct dgcn_genconv_params {
  * x_dst (N, C) the rows of the destinations this call owns (may be NULL when neither
  * msg_norm nor add_residual is set).
  * edge_attr (E, C) in edge_index order or NULL.  out (N, C). */
+/* Long rows ("hubs" of power-law graphs): rows of in-degree >= min_degree are cut into segments of
+ * seg_edges edges.  dgcn_csr_hub_rows lists them once per graph, entirely on the device:
+ *   items  (2 * max_items int32): (row, segment) pairs, max_items = E / seg_edges + N_hub <= E/seg + E/min_degree + 1
+ *   rows   (3 * max_rows  int32): (row, first item, #segments), max_rows <= E / min_degree + 1
+ *   counts (2 int32): number of items, number of rows.
+ * Given to dgcn_genconv_aggregate (with `partial`, a scratch of items * 3 * C floats) those rows are
+ * aggregated by one CTA per segment plus a fixed-order merge instead of one warp per row. */
+typedef struct dgcn_csr_hubs {
+  const int32_t* items;
+  const int32_t* rows;
+  const int32_t* counts;
+  int32_t min_degree;
+  int32_t seg_edges;
+  float* partial;
+} dgcn_csr_hubs;
+int dgcn_csr_hub_rows(const int32_t* rowptr, int64_t N, int64_t E, int32_t min_degree, int32_t seg_edges,
+                      int32_t* items, int32_t* rows, int32_t* counts, dgcn_stream_t stream);
+
 int dgcn_genconv_aggregate(const float* x_src, const float* x_dst, int64_t N, int64_t C,
                            const int32_t* rowptr, const int32_t* src, const int32_t* eid,
-                           const float* edge_attr, const dgcn_genconv_params* prm, float* out,
+                           const float* edge_attr, const dgcn_genconv_params* prm,
+                           const dgcn_csr_hubs* hubs /* may be NULL */, float* out,
                            dgcn_stream_t stream);
 
 /* Gradient of dgcn_genconv_aggregate w.r.t. x (both roles), edge_attr and the

@@ -38,6 +38,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_native.BasicConvC) == 96
     assert ctypes.sizeof(_native.DilationC) == 24
     assert ctypes.sizeof(_native.GenconvParamsC) == 80
+    assert ctypes.sizeof(_native.CsrHubsC) == 40
 
 
 def test_no_cpu_fallback():

@@ -41,7 +41,7 @@ def test_csr_build_is_stable_and_complete():
     g = torch.Generator().manual_seed(0)
     for (n, e) in [(1, 5), (10, 0), (300, 3050), (70000, 200000), (5, 4099)]:
         ei = torch.stack((torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)))
-        rowptr, src, eid = _native.csr_build(ei.cuda(), n)
+        rowptr, src, eid = _native.csr_build(ei.cuda(), n)[:3]
         order = torch.sort(ei[1], stable=True).indices
         assert torch.equal(eid.cpu().long()[:e], order)
         assert torch.equal(src.cpu().long()[:e], ei[0][order])
@@ -126,3 +126,31 @@ def test_arxiv_shape_properties():
     sub = ei[:, keep]
     ref = osp.aggregate(osp.message(x, sub), sub[1], N, "softmax", 0.1)[rows]
     torch.testing.assert_close(m1.cpu()[rows], ref, rtol=RTOL, atol=ATOL)
+
+
+def test_power_law_graph_hub_rows():
+    """dst ~ Zipf: a few destinations collect tens of thousands of edges (SURVEY.md 8d load-balance
+    stress).  Long rows take the CTA-per-row kernel; results must not depend on which kernel ran."""
+    from deep_gcns_torch_b200 import _native
+    from deep_gcns_torch_b200.gcn_lib import sparse as S
+    g = torch.Generator().manual_seed(0)
+    N, E, C = 20000, 400000, 128
+    u = torch.rand(E, generator=g).clamp_min(1e-9)
+    dst = (u.pow(-1.0 / 0.5) - 1).clamp(max=N - 1).long()          # heavy tail: node 0..few are hubs
+    ei = torch.stack((torch.randint(0, N, (E,), generator=g), dst))
+    deg = torch.bincount(dst, minlength=N)
+    assert int(deg.max()) > 20000 and int((deg >= _native.HUB_MIN_DEGREE).sum()) >= 3
+    x = torch.randn(N, C, generator=g)
+    for aggr in ("softmax", "softmax_sum", "power", "mean", "max"):
+        torch.manual_seed(0)
+        conv = S.GENConv(C, C, aggr=aggr, t=0.2, p=1.5, y=0.3, msg_norm=True, mlp_layers=1, norm="layer").eval()
+        ref = osp.genconv_forward(conv, x, ei, dtype=torch.float64).float()
+        conv = conv.cuda()
+        with torch.no_grad():
+            y = conv(x.cuda(), ei.cuda())
+        torch.testing.assert_close(y.cpu(), ref, rtol=2e-3, atol=2e-4)
+        csr = _native.csr_build(ei.cuda(), N)
+        prm, keep = _native.genconv_params(aggr, 0.2, 1.5, 0.3, 1e-7, None, add_residual=False)
+        with_hubs = _native.genconv_aggregate(x.cuda(), x.cuda(), csr, prm)
+        no_hubs = _native.genconv_aggregate(x.cuda(), x.cuda(), csr[:3], prm)
+        torch.testing.assert_close(with_hubs, no_hubs, rtol=1e-4, atol=1e-5)
