@@ -48,6 +48,32 @@ class ResGCN28(torch.nn.Module):
         return self.prediction(torch.cat((fusion, feats), dim=1)).squeeze(-1)
 
 
+class MRGCN28(torch.nn.Module):
+    """examples/modelnet_cls/architecture.py:11-81 restated: DilatedKnnGraph head (self excluded) +
+    27 ResDynBlock2d('mr', dilation 1..27) + fusion / pooling / prediction."""
+
+    def __init__(self, D, in_channels=3, n_classes=40, k=20, channels=64, n_blocks=28, emb=1024):
+        super().__init__()
+        self.n_blocks = n_blocks
+        self.knn = D.DilatedKnnGraph(k, 1, False, 0.0)
+        self.head = D.GraphConv2d(in_channels, channels, "mr", "relu", "batch", bias=False)
+        self.backbone = torch.nn.Sequential(*[D.ResDynBlock2d(channels, k, i + 1, "mr", "relu", "batch", True, False, 0.0,
+                                                              "matrix") for i in range(n_blocks - 1)])
+        self.fusion_block = D.BasicConv([channels * n_blocks, emb], "leakyrelu", "batch", bias=False)
+        self.prediction = torch.nn.Sequential(D.BasicConv([emb * 2, 512], "leakyrelu", "batch"),
+                                              D.BasicConv([512, 256], "leakyrelu", "batch"),
+                                              D.BasicConv([256, n_classes], None, None))
+
+    def forward(self, inputs):
+        feats = [self.head(inputs, self.knn(inputs[:, 0:3]))]
+        for i in range(self.n_blocks - 1):
+            feats.append(self.backbone[i](feats[-1]))
+        fusion = self.fusion_block(torch.cat(feats, dim=1))
+        x1 = F.adaptive_max_pool2d(fusion, 1)
+        x2 = F.adaptive_avg_pool2d(fusion, 1)
+        return self.prediction(torch.cat((x1, x2), dim=1)).squeeze(-1).squeeze(-1)
+
+
 class DeeperGCN(torch.nn.Module):
     def __init__(self, S, layers=56, hidden=128, in_channels=128, tasks=40):
         super().__init__()
@@ -98,6 +124,26 @@ def main():
         edges = 28 * 16 * 4096 * 20
         out["c2_resgcn28"] = {"backbone_ms": ms_bb, "model_ms": ms_all, "edges_per_s_backbone": edges / (ms_bb * 1e-3),
                               "per_layer": per_layer}
+    if "c4" in a.which:      # per-GPU share of config 4 (B=64 over 8 GPUs): forward + backward + SGD step
+        torch.manual_seed(0)
+        model = MRGCN28(D).to(dev).train()
+        inputs = torch.rand(8, 3, 1024, 1, generator=g).to(dev)
+        labels = torch.randint(0, 40, (8,), generator=g).to(dev)
+        opt = torch.optim.SGD(model.parameters(), lr=0.01)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = F.cross_entropy(model(inputs), labels)
+            loss.backward()
+            opt.step()
+            return loss
+        l0 = float(step())
+        ms = timeit(step, 3)
+        with torch.no_grad():
+            model.eval()
+            ms_fwd = timeit(lambda: model(inputs), 3)
+        out["c4_mrgcn28_train_step_B8"] = {"fwd_bwd_step_ms": ms, "eval_fwd_ms": ms_fwd, "first_loss": l0,
+                                           "edges_per_s_fwd_bwd": 28 * 8 * 1024 * 20 / (ms * 1e-3)}
     if "c3" in a.which:
         N = 169343
         s, d = torch.randint(0, N, (1166243,), generator=g), torch.randint(0, N, (1166243,), generator=g)
