@@ -92,9 +92,15 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
     const size_t smem = sizeof(TcSmem) + 1024;
 #define DGCN_TC_LAUNCH(KPV)                                                                                   \
   do {                                                                                                        \
-    DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_tc_kernel<KPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                       static_cast<int>(smem)));                                              \
-    knn_tc_kernel<KPV><<<grid, TC_THREADS, smem, stream>>>(t);                                                \
+    if (N <= 4096) {                                                                                          \
+      DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_tc_kernel<KPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         static_cast<int>(smem)));                                            \
+      knn_tc_kernel<KPV, true><<<grid, TC_THREADS, smem, stream>>>(t);                                        \
+    } else {                                                                                                  \
+      DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_tc_kernel<KPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         static_cast<int>(smem)));                                            \
+      knn_tc_kernel<KPV, false><<<grid, TC_THREADS, smem, stream>>>(t);                                       \
+    }                                                                                                         \
   } while (0)
     // list length per warpgroup = K + certification margin
     if (K <= 12) DGCN_TC_LAUNCH(16);

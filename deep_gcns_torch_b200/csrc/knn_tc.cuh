@@ -234,7 +234,20 @@ __device__ __forceinline__ void reg_insert(uint32_t (&k)[KP], uint32_t (&v)[KP],
   v[0] = lt[0] ? nv : v[0];
 }
 
+// Packed variant for N <= 4096: one register per entry = (float bits of the approximate squared
+// distance, low 12 mantissa bits replaced by the candidate index).  Truncating the distance can only
+// lower the certificate's cut, never invalidate it.
 template <int KP>
+__device__ __forceinline__ void reg_insert_packed(uint32_t (&k)[KP], uint32_t nk) {
+  bool lt[KP];
+#pragma unroll
+  for (int i = 0; i < KP; ++i) lt[i] = nk < k[i];
+#pragma unroll
+  for (int i = KP - 1; i > 0; --i) k[i] = lt[i - 1] ? k[i - 1] : (lt[i] ? nk : k[i]);
+  k[0] = lt[0] ? nk : k[0];
+}
+
+template <int KP, bool PACKED>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // SWIZZLE_128B atoms must sit on 1024-byte boundaries of the shared address space
@@ -276,12 +289,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
 
   const int qg = q0 + r;
   // the KP best approximate keys of THIS warpgroup's tiles, ascending, in registers
-  uint32_t lk[KP], lv[KP];
+  uint32_t lk[KP], lv[PACKED ? 1 : KP];
 #pragma unroll
   for (int i = 0; i < KP; ++i) {
     lk[i] = 0xFFFFFFFFu;
-    lv[i] = 0xFFFFFFFFu;
+    if (!PACKED) lv[i] = 0xFFFFFFFFu;
   }
+  const float sqq = __ldg(sqb + qg);
   float tau_own = __uint_as_float(0x7FC00000u);   // NaN admits everything until the list is full
   uint64_t* const cb0 = sm.cbuf + tid;            // private buffer: slots cb0[0], cb0[TC_THREADS], ...
   const uint32_t cb_addr0 = smem_u32(cb0);
@@ -296,13 +310,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
       uint32_t nk = 0xFFFFFFFFu, nv = 0u;
       if (e < cnt) {
         const uint64_t kv = cb0[e * TC_THREADS];     // low word = index, high word = float key bits
-        nk = float_to_ordered(__uint_as_float(static_cast<uint32_t>(kv >> 32)));
         nv = static_cast<uint32_t>(kv);
+        if (PACKED) {
+          const float d2 = fmaxf(__uint_as_float(static_cast<uint32_t>(kv >> 32)) + sqq, 0.f);
+          nk = (__float_as_uint(d2) & 0xFFFFF000u) | (nv & 0xFFFu);
+        } else {
+          nk = float_to_ordered(__uint_as_float(static_cast<uint32_t>(kv >> 32)));
+        }
       }
-      if (nk < lk[KP - 1]) reg_insert<KP>(lk, lv, nk, nv);
+      if (nk < lk[KP - 1]) {
+        if constexpr (PACKED) reg_insert_packed<KP>(lk, nk);
+        else reg_insert<KP>(lk, lv, nk, nv);
+      }
     }
     cb_addr = cb_addr0;
-    tau_own = ordered_to_float(lk[KP - 1]);      // NaN while the list is not full
+    if (PACKED) {   // admission in key units (distance minus |x_i|^2), one truncation step above the last entry
+      tau_own = lk[KP - 1] == 0xFFFFFFFFu ? __uint_as_float(0x7FC00000u)
+                                          : __uint_as_float((lk[KP - 1] & 0xFFFFF000u) + 0x1000u) - sqq;
+    } else {
+      tau_own = ordered_to_float(lk[KP - 1]);      // NaN while the list is not full
+    }
     if (tau_own == tau_own) sm.tau_pub[wg][r] = tau_own;
   };
 
@@ -407,19 +434,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
 
   // ---- per list: exact re-rank of the listed candidates (fp32 FMA chain, k ascending) --------------
   uint64_t* list = reinterpret_cast<uint64_t*>(sm.work) + static_cast<size_t>(wg) * KP * TILE;   // [KP][TILE]
-  sm.cut[wg][r] = (lk[KP - 1] == 0xFFFFFFFFu) ? INFINITY : ordered_to_float(lk[KP - 1]);   // approx key, no |x_i|^2
+  // lower bound of every unlisted candidate's approximate key (PACKED: of its squared distance)
+  sm.cut[wg][r] = (lk[KP - 1] == 0xFFFFFFFFu) ? INFINITY
+                  : (PACKED ? __uint_as_float(lk[KP - 1] & 0xFFFFF000u) : ordered_to_float(lk[KP - 1]));
   const int C = a.C;
   const float* xtb = t.xt + static_cast<int64_t>(b) * N * C;
   float xq[TC_MAX_C];
 #pragma unroll
   for (int c = 0; c < TC_MAX_C; ++c) xq[c] = c < C ? __ldg(xtb + static_cast<int64_t>(qg) * C + c) : 0.f;
-  const float sqq = __ldg(sqb + qg);
   {
     int e = 0;
 #pragma unroll
     for (int u = 0; u < KP; ++u) {
-      if (lk[u] != 0xFFFFFFFFu || lv[u] != 0xFFFFFFFFu) {
-        const int j = static_cast<int>(lv[u]);
+      if (PACKED ? (lk[u] != 0xFFFFFFFFu) : (lk[u] != 0xFFFFFFFFu || lv[u] != 0xFFFFFFFFu)) {
+        const int j = static_cast<int>(PACKED ? (lk[u] & 0xFFFu) : lv[u]);
         const float* xj = xtb + static_cast<int64_t>(j) * C;
         float acc = 0.f;
         if ((C & 3) == 0) {
@@ -487,7 +515,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
       // ~4*Cpad fp32 tensor-core accumulations and Cpad FMA-chain roundings (2^-23 each), the final additions.
       const float eps = (2.0f * (2.158e-5f + (5.0f * Cpad + 8.0f) * 1.1921e-7f)) * sqrtf(sqq * smax) +
                         4.768e-7f * (sqq + smax);
-      ok = (dk + eps < cut + sqq);
+      ok = (dk + eps < (PACKED ? cut : cut + sqq));
     }
     sm.ok[r] = ok ? 1 : 0;
     if (!ok) {
