@@ -275,8 +275,8 @@ def run_native(args):
         "e2e": {"value": EDGES_PER_STEP * world * args.steps / (ms_e2e * 1e-3), "unit": "edges/s",
                 "h2d_bytes_per_step": B * C * N * 4, "d2h_bytes_per_step": B * C * N * 4,
                 "ms_per_step": ms_e2e / args.steps},
-        # pack_edge_weights, node_pq, sqnorm, split_bf16, to_node_major, sqmax, knn_tc, knn_exact_rows per step
-        "gpu_launches": 8 * args.steps,
+        # pack_edge_weights, node_pq, tc_prologue, knn_tc, knn_exact_rows per step
+        "gpu_launches": 5 * args.steps,
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "knn_tc_kernel<24> (tcgen05 bf16x3 pre-filter + exact fp32 re-rank + "
                                                  "certificate + fused EdgeConv gather/max)",

@@ -67,16 +67,12 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
   int* fail = ws.take<int>(static_cast<size_t>(B) * N + 64);
   if (!ws.ok) return DGCN_ERR_WORKSPACE;
   DGCN_CUDA_TRY(cudaMemsetAsync(fail, 0, 256, stream));
-  split_bf16_kernel<<<dim3(ceil_div(N, 256), cpad, B), 256, 0, stream>>>(a.x, a.sb, a.sc, C, cpad, N, planes);
+  DGCN_CUDA_TRY(cudaMemsetAsync(sqmax, 0, static_cast<size_t>(B) * 4, stream));
+  // sq, bf16 planes, node-major copy and max |x|^2 in one pass over x (sq overwrites what the caller computed)
+  tc_prologue_kernel<<<dim3(ceil_div(N, 32), B), 256, 0, stream>>>(a.x, a.sb, a.sc, C, cpad, N, const_cast<float*>(a.sq),
+                                                               planes, xt ? nullptr : xt_own, sqmax);
   DGCN_LAUNCH_CHECK();
-  if (!xt) {
-    to_node_major_kernel<<<dim3(ceil_div(N, 32), ceil_div(C, 32), B), dim3(32, 8), 0, stream>>>(a.x, a.sb, a.sc, C, N,
-                                                                                              xt_own);
-    DGCN_LAUNCH_CHECK();
-    xt = xt_own;
-  }
-  sqmax_kernel<<<B, 256, 0, stream>>>(a.sq, N, sqmax);
-  DGCN_LAUNCH_CHECK();
+  if (!xt) xt = xt_own;
   TcArgs t{};
   t.a = a;
   t.planes = planes;
@@ -124,11 +120,11 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
   float* sq = ws.take<float>(static_cast<size_t>(B) * N);
   if (!ws.ok) return DGCN_ERR_WORKSPACE;
   a.sq = sq;
-  sqnorm_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(a.x, a.sb, a.sc, a.C, N, sq);
-  DGCN_LAUNCH_CHECK();
   const bool train_wide = a.epi.mode == EPI_EDGE && a.epi.norm == DGCN_NORM_BATCH_TRAIN && a.epi.c_out > 128;
   if (tc_enabled() && tc_shape_ok(a.C, N, K) && a.k <= SEL_LD && !train_wide)
     return launch_knn_tc(a, ws, stream, a.epi.mode == EPI_MR ? a.epi.xt : nullptr, n_partial);
+  sqnorm_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(a.x, a.sb, a.sc, a.C, N, sq);
+  DGCN_LAUNCH_CHECK();
   const dim3 grid(ceil_div(N, TILE), B);
   if (n_partial) *n_partial = K <= SMALL_K_MAX ? static_cast<int64_t>(grid.x) * grid.y : static_cast<int64_t>(B) * N;
   if (K <= 32) {

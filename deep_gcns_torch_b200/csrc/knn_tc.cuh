@@ -146,6 +146,45 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t sb, int64
   base[plane] = mid;
 }
 
+// One pass over x for everything the tensor-core path needs: sq (B,N) (same FMA chain as sqnorm_kernel),
+// the bf16 planes, the node-major copy xt (optional) and the per-cloud max of sq (atomicMax on the bits of
+// a non-negative float; sqmax must be zero-initialised).  Block = 32 points x all channels (C <= 64).
+__global__ void __launch_bounds__(256) tc_prologue_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C,
+                                                         int Cpad, int N, float* __restrict__ sq,
+                                                         __nv_bfloat16* __restrict__ planes, float* __restrict__ xt,
+                                                         float* __restrict__ sqmax) {
+  __shared__ float tile[TC_MAX_C][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int b = blockIdx.y, n0 = blockIdx.x * 32, n = n0 + tx;
+  const int64_t plane = static_cast<int64_t>(Cpad) * N;
+  __nv_bfloat16* pb = planes + static_cast<int64_t>(b) * TC_PLANES * plane;
+  for (int c = ty; c < Cpad; c += 8) {
+    float v = 0.f;
+    if (c < C && n < N) v = __ldg(x + b * sb + c * sc + n);
+    if (c < C) tile[c][tx] = v;
+    if (n < N) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      pb[static_cast<int64_t>(c) * N + n] = hi;
+      pb[plane + static_cast<int64_t>(c) * N + n] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+  }
+  __syncthreads();
+  if (ty == 0) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(tile[c][tx], tile[c][tx], s);
+    if (n < N) sq[static_cast<int64_t>(b) * N + n] = s;
+    float m = n < N ? s : 0.f;
+    m = warp_max(m);
+    if (tx == 0) atomicMax(reinterpret_cast<unsigned int*>(sqmax + b), __float_as_uint(m));
+  }
+  if (xt) {
+    for (int i = threadIdx.x; i < 32 * C; i += 256) {
+      const int rr = i / C, c = i % C;
+      if (n0 + rr < N) xt[(static_cast<int64_t>(b) * N + n0 + rr) * C + c] = tile[c][rr];
+    }
+  }
+}
+
 // sq (B,N) as in sqnorm_kernel plus the per-cloud maximum (for the certification bound)
 __global__ void sqmax_kernel(const float* __restrict__ sq, int N, float* __restrict__ sqmax) {
   __shared__ float red[32];
