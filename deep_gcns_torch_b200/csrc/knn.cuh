@@ -86,6 +86,20 @@ __device__ __forceinline__ void edge_query(const Epilogue& e, int64_t node0, int
   const float p = __ldg(e.pq + (node0 + q) * ld + c);
   const float* qbase = e.pq + node0 * ld + e.c_out + c;
   int l = 0;
+  for (; l + 8 <= k; l += 8) {   // eight independent row reads in flight per lane
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(qbase + static_cast<int64_t>(sel[l + u]) * ld);
+#pragma unroll
+    for (int u = 0; u < 8; u += 4) {
+      float a0 = act_apply(p + v[u], slope), a1 = act_apply(p + v[u + 1], slope);
+      float a2 = act_apply(p + v[u + 2], slope), a3 = act_apply(p + v[u + 3], slope);
+      vmax = fmaxf(fmaxf(vmax, a0), fmaxf(a1, fmaxf(a2, a3)));
+      vmin = fminf(fminf(vmin, a0), fminf(a1, fminf(a2, a3)));
+      s1 += (a0 + a1) + (a2 + a3);
+      s2 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+  }
   for (; l + 4 <= k; l += 4) {
     float v0 = __ldg(qbase + static_cast<int64_t>(sel[l + 0]) * ld);
     float v1 = __ldg(qbase + static_cast<int64_t>(sel[l + 1]) * ld);

@@ -482,32 +482,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
 #pragma unroll
   for (int c = 0; c < TC_MAX_C; ++c) xq[c] = c < C ? __ldg(xtb + static_cast<int64_t>(qg) * C + c) : 0.f;
   {
+    // pass 1: exact distances of all listed candidates - pure loads + FMA chains, no shared-memory
+    // traffic in between, so the loads of the next candidates overlap the chains of the current one
+    float dex[KP];
+#pragma unroll
+    for (int u = 0; u < KP; ++u) {
+      const bool valid = PACKED ? (lk[u] != 0xFFFFFFFFu) : (lk[u] != 0xFFFFFFFFu || lv[u] != 0xFFFFFFFFu);
+      const int j = valid ? static_cast<int>(PACKED ? (lk[u] & 0xFFFu) : lv[u]) : qg;
+      const float* xj = xtb + static_cast<int64_t>(j) * C;
+      float acc = 0.f;
+      if ((C & 3) == 0) {
+#pragma unroll
+        for (int c = 0; c < TC_MAX_C; c += 4) {
+          if (c < C) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(xj + c));
+            acc = fmaf(xq[c], w.x, acc);
+            acc = fmaf(xq[c + 1], w.y, acc);
+            acc = fmaf(xq[c + 2], w.z, acc);
+            acc = fmaf(xq[c + 3], w.w, acc);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < TC_MAX_C; ++c)
+          if (c < C) acc = fmaf(xq[c], __ldg(xj + c), acc);
+      }
+      dex[u] = (sqq + (-2.0f * acc)) + __ldg(sqb + j);
+    }
+    // pass 2: insertion by exact key into the exact-sorted prefix [0, e)
     int e = 0;
 #pragma unroll
     for (int u = 0; u < KP; ++u) {
-      if (PACKED ? (lk[u] != 0xFFFFFFFFu) : (lk[u] != 0xFFFFFFFFu || lv[u] != 0xFFFFFFFFu)) {
-        const int j = static_cast<int>(PACKED ? (lk[u] & 0xFFFu) : lv[u]);
-        const float* xj = xtb + static_cast<int64_t>(j) * C;
-        float acc = 0.f;
-        if ((C & 3) == 0) {
-#pragma unroll
-          for (int c = 0; c < TC_MAX_C; c += 4) {
-            if (c < C) {
-              const float4 w = __ldg(reinterpret_cast<const float4*>(xj + c));
-              acc = fmaf(xq[c], w.x, acc);
-              acc = fmaf(xq[c + 1], w.y, acc);
-              acc = fmaf(xq[c + 2], w.z, acc);
-              acc = fmaf(xq[c + 3], w.w, acc);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < TC_MAX_C; ++c)
-            if (c < C) acc = fmaf(xq[c], __ldg(xj + c), acc);
-        }
-        const float d = (sqq + (-2.0f * acc)) + __ldg(sqb + j);
-        const uint64_t key = make_key(d, static_cast<uint32_t>(j));
-        int i = e;   // insertion by exact key into the exact-sorted prefix [0, e)
+      const bool valid = PACKED ? (lk[u] != 0xFFFFFFFFu) : (lk[u] != 0xFFFFFFFFu || lv[u] != 0xFFFFFFFFu);
+      if (valid) {
+        const uint32_t j = PACKED ? (lk[u] & 0xFFFu) : lv[u];
+        const uint64_t key = make_key(dex[u], j);
+        int i = e;
         while (i > 0) {
           const uint64_t prev = list[(i - 1) * TILE + r];
           if (prev < key) break;
