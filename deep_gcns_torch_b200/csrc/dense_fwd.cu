@@ -3,6 +3,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "knn_tc.cuh"
 
 namespace dgcn {
@@ -20,7 +22,7 @@ static size_t knn_slab_clouds(int64_t B, int64_t N) {
   return static_cast<size_t>(nb);
 }
 
-constexpr int TC_FALLBACK_GRID = 64;   // CTAs (x8 warps) of the exact completion kernel
+constexpr int TC_FALLBACK_GRID = 148;  // CTAs of the exact completion kernel (one uncertified query at a time each)
 
 static bool tc_shape_ok(int64_t C, int64_t N, int64_t K) {
   return K <= TC_K_MAX && C <= TC_MAX_C && N >= TILE && (N % TILE) == 0;
@@ -85,9 +87,21 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
   const int64_t n_cta = static_cast<int64_t>(grid.x) * grid.y;
   {
     KernelTimer timer(stream, "knn");
-    const size_t smem = sizeof(TcSmem) + 1024;
+    const int nch = a.epi.mode == EPI_MR ? a.epi.c_in : a.epi.c_out;
+    t.wide = epilogue_wide_ok(a) ? 1 : 0;
+    t.flush_early = TC_FLUSH_EARLY;
+    t.flush_late = TC_FLUSH_LATE;
+    if (const char* fe = getenv("DGCN_TC_FLUSH")) {   // tuning hook: "early,late", each in [1, 24]
+      int e1 = 0, l1 = 0;
+      if (sscanf(fe, "%d,%d", &e1, &l1) == 2 && e1 >= 1 && e1 <= 24 && l1 >= 1 && l1 <= 24) {
+        t.flush_early = e1;
+        t.flush_late = l1;
+      }
+    }
 #define DGCN_TC_LAUNCH(KPV)                                                                                   \
   do {                                                                                                        \
+    t.work_bytes = static_cast<int>(tc_work_bytes(KPV, a.k, t.wide != 0, nch));                               \
+    const size_t smem = static_cast<size_t>(t.work_bytes) + sizeof(TcTail) + 1024;                            \
     if (N <= 4096) {                                                                                          \
       DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_tc_kernel<KPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          static_cast<int>(smem)));                                            \
@@ -98,10 +112,11 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
       knn_tc_kernel<KPV, false><<<grid, TC_THREADS, smem, stream>>>(t);                                       \
     }                                                                                                         \
   } while (0)
-    // list length per warpgroup = K + certification margin
-    if (K <= 12) DGCN_TC_LAUNCH(16);
-    else if (K <= 20) DGCN_TC_LAUNCH(24);
-    else if (K <= 28) DGCN_TC_LAUNCH(32);
+    // list length = K + certification margin
+    // (a margin of 4 ranks leaves ~1e-5 of the queries of a random 64-d cloud uncertified, 8 ranks none)
+    if (K <= 9) DGCN_TC_LAUNCH(16);
+    else if (K <= 20) DGCN_TC_LAUNCH(28);
+    else if (K <= 32) DGCN_TC_LAUNCH(40);
     else DGCN_TC_LAUNCH(56);
 #undef DGCN_TC_LAUNCH
     DGCN_LAUNCH_CHECK();
@@ -109,7 +124,7 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
     knn_exact_rows_kernel<<<TC_FALLBACK_GRID, 256, 0, stream>>>(a, t.fail_count, t.fail_list, extra);
     DGCN_LAUNCH_CHECK();
   }
-  if (n_partial) *n_partial = n_cta + TC_FALLBACK_GRID * 8;
+  if (n_partial) *n_partial = n_cta + TC_FALLBACK_GRID;
   return DGCN_OK;
 }
 
@@ -490,7 +505,7 @@ static ConvPlan conv_plan(int conv, int64_t B, int64_t ci, int64_t co, int64_t N
     p.bk = 2 * co;
     p.pq = B * N * 2 * co;
     p.out_min = B * co * N;
-    int64_t tiles = fused ? (K <= SMALL_K_MAX ? ceil_div(N, TILE) * B + TC_FALLBACK_GRID * 8 : B * N) : ceil_div(N, 32) * B;
+    int64_t tiles = fused ? (K <= SMALL_K_MAX ? ceil_div(N, TILE) * B + TC_FALLBACK_GRID : B * N) : ceil_div(N, 32) * B;
     p.n_partial = tiles;
     p.partial = tiles * 2 * co;
   } else {

@@ -165,7 +165,7 @@ constexpr int STAGE_LD = TILE + 1;         // padded staging row (bank-conflict 
 template <int NW>
 __device__ __forceinline__ void cta_epilogue(const KnnArgs& a, int b, int q0, const uint64_t* list,
                                              const unsigned char* ok, int* sel, float* stage_max,
-                                             float* stage_min, int cta) {
+                                             float* stage_min, int cta, int sel_ld = SEL_LD) {
   const Epilogue& e = a.epi;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N, k = a.k;
@@ -177,7 +177,7 @@ __device__ __forceinline__ void cta_epilogue(const KnnArgs& a, int b, int q0, co
     const bool live = qg < N && (ok == nullptr || ok[ql]);
     for (int l = lane; l < k; l += 32) {
       int idx = static_cast<int>(static_cast<uint32_t>(list[keep_rank(a, l) * TILE + ql]));
-      sel[ql * SEL_LD + l] = idx;
+      sel[ql * sel_ld + l] = idx;
       if (live) {
         int64_t o = (node0 + qg) * k + l;
         if (e.nbr) e.nbr[o] = idx;
@@ -205,7 +205,7 @@ __device__ __forceinline__ void cta_epilogue(const KnnArgs& a, int b, int q0, co
       if (qg >= N || (ok != nullptr && !ok[ql])) continue;
       if (e.mode == EPI_EDGE) {
         float vmax, vmin;
-        edge_query(e, node0, qg, &sel[ql * SEL_LD], k, c, slope, vmax, vmin, s1, s2);
+        edge_query(e, node0, qg, &sel[ql * sel_ld], k, c, slope, vmax, vmin, s1, s2);
         if (train) {
           stage_max[lane * STAGE_LD + ql] = vmax;
           stage_min[lane * STAGE_LD + ql] = vmin;
@@ -213,7 +213,7 @@ __device__ __forceinline__ void cta_epilogue(const KnnArgs& a, int b, int q0, co
           stage_max[lane * STAGE_LD + ql] = bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt);
         }
       } else {
-        stage_max[lane * STAGE_LD + ql] = mr_query(e, node0, qg, &sel[ql * SEL_LD], k, c);
+        stage_max[lane * STAGE_LD + ql] = mr_query(e, node0, qg, &sel[ql * sel_ld], k, c);
       }
     }
     if (train) {
@@ -237,6 +237,166 @@ __device__ __forceinline__ void cta_epilogue(const KnnArgs& a, int b, int q0, co
       if (c0 + cc < nch) e.partial[(static_cast<int64_t>(cta) * 2 + which) * nch + c0 + cc] = s;
     }
     __syncthreads();
+  }
+}
+
+
+// ---- wide CTA-level consumer ------------------------------------------------------------------
+// Same contract as cta_epilogue for channel counts nch in {32, 64, 128} (nch = c_out for EdgeConv,
+// c_in for MRConv) and N % 8 == 0: a group of G = nch/4 lanes owns one query and reads every selected
+// row as ONE float4 per lane, up to ten rows in flight, so a warp keeps 32 x 10 x 16 B outstanding
+// instead of 8 x 128 B.  A group walks eight consecutive queries and then stores its four channels as
+// full 32-byte sectors; no shared-memory staging.  sel: int [TILE][sel_ld]; red: float [NW][2][nch]
+// (train statistics only).  Each warp only touches the sel rows of its own queries.
+__host__ __device__ __forceinline__ bool epilogue_wide_ok(const KnnArgs& a) {
+  const Epilogue& e = a.epi;
+  if (e.mode == EPI_INDEX) return true;
+  const int nch = (e.mode == EPI_EDGE) ? e.c_out : e.c_in;
+  const float* rows = (e.mode == EPI_EDGE) ? e.pq : e.xt;
+  return (nch == 32 || nch == 64 || nch == 128) && (a.N & 7) == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0;
+}
+
+template <int NW, bool TRAIN>
+__device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q0, const uint64_t* list,
+                                                  const unsigned char* ok, int* sel, int sel_ld, float* red,
+                                                  int cta) {
+  const Epilogue& e = a.epi;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = a.N, k = a.k;
+  constexpr int QPW = TILE / NW;            // queries per warp
+  static_assert(QPW == 32, "wide consumer: one warp per 32 queries");
+  const int64_t node0 = static_cast<int64_t>(b) * N;
+  for (int qq = 0; qq < QPW; ++qq) {
+    const int ql = warp * QPW + qq;
+    const int qg = q0 + ql;
+    const bool live = qg < N && ok[ql];
+    for (int l = lane; l < k; l += 32) {
+      const int idx = static_cast<int>(static_cast<uint32_t>(list[keep_rank(a, l) * TILE + ql]));
+      sel[ql * sel_ld + l] = idx;
+      if (live) {
+        const int64_t o = (node0 + qg) * k + l;
+        if (e.nbr) e.nbr[o] = idx;
+        if (e.edge_index) {
+          e.edge_index[o] = idx;
+          e.edge_index[static_cast<int64_t>(a.B) * N * k + o] = qg;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (e.mode == EPI_INDEX) return;
+
+  const bool edge = e.mode == EPI_EDGE;
+  const int nch = edge ? e.c_out : e.c_in;
+  const int ld = edge ? 2 * e.c_out : e.c_in;
+  const int G = nch >> 2, slots = 32 / G, per_slot = QPW / slots;     // 8 | per_slot
+  const int g = lane & (G - 1), slot = lane / G;
+  const float* rows = (edge ? e.pq + e.c_out : e.xt) + node0 * ld + 4 * g;   // neighbour rows (Q half / x rows)
+  const float* self = (edge ? e.pq : e.xt) + node0 * ld + 4 * g;             // centre rows (P half / x rows)
+  const float slope = edge ? epi_slope(e) : 0.f;
+  float bs[4] = {1.f, 1.f, 1.f, 1.f}, bt[4] = {0.f, 0.f, 0.f, 0.f};
+  if (edge && !TRAIN) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bn_affine(e, 4 * g + i, bs[i], bt[i]);
+  }
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  float* dst = edge ? e.out : e.r_out;
+  for (int round = 0; round < per_slot; round += 8) {
+    const int qlb = warp * QPW + slot * per_slot + round;    // first of eight consecutive queries
+    float res[8][4], res2[TRAIN ? 8 : 1][4];
+    bool all_live = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ql = qlb + i, qg = q0 + ql;
+      const bool live = qg < N && ok[ql];
+      all_live = all_live && live;
+      float vmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      float vmin[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        p = __ldg(reinterpret_cast<const float4*>(self + static_cast<int64_t>(qg) * ld));
+        const int* srow = sel + ql * sel_ld;
+        for (int l0 = 0; l0 < k; l0 += 10) {
+          float4 v[10];
+#pragma unroll
+          for (int u = 0; u < 10; ++u) {
+            const int idx = srow[min(l0 + u, k - 1)];
+            v[u] = __ldg(reinterpret_cast<const float4*>(rows + static_cast<int64_t>(idx) * ld));
+          }
+#pragma unroll
+          for (int u = 0; u < 10; ++u) {
+            if (l0 + u < k) {
+              const float w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+              const float pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float av = edge ? act_apply(pp[c] + w[c], slope) : w[c];
+                vmax[c] = fmaxf(vmax[c], av);
+                if (edge) vmin[c] = fminf(vmin[c], av);
+                if (TRAIN) {
+                  s1[c] += av;
+                  s2[c] = fmaf(av, av, s2[c]);
+                }
+              }
+            }
+          }
+        }
+      }
+      const float pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (!edge) res[i][c] = vmax[c] - pp[c];
+        else if (TRAIN) {
+          res[i][c] = vmax[c];
+          res2[i][c] = vmin[c];
+        } else {
+          res[i][c] = bs[c] >= 0.f ? fmaf(bs[c], vmax[c], bt[c]) : fmaf(bs[c], vmin[c], bt[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t o = (static_cast<int64_t>(b) * nch + 4 * g + c) * N + q0 + qlb;
+      if (all_live) {
+        *reinterpret_cast<float4*>(dst + o) = make_float4(res[0][c], res[1][c], res[2][c], res[3][c]);
+        *reinterpret_cast<float4*>(dst + o + 4) = make_float4(res[4][c], res[5][c], res[6][c], res[7][c]);
+        if (TRAIN) {
+          *reinterpret_cast<float4*>(e.out_min + o) = make_float4(res2[0][c], res2[1][c], res2[2][c], res2[3][c]);
+          *reinterpret_cast<float4*>(e.out_min + o + 4) =
+              make_float4(res2[TRAIN ? 4 : 0][c], res2[TRAIN ? 5 : 0][c], res2[TRAIN ? 6 : 0][c], res2[TRAIN ? 7 : 0][c]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ql = qlb + i;
+          if (q0 + ql < N && ok[ql]) {
+            dst[o + i] = res[i][c];
+            if (TRAIN) e.out_min[o + i] = res2[TRAIN ? i : 0][c];
+          }
+        }
+      }
+    }
+  }
+  if (TRAIN) {
+    // fixed-order reduction: slots of a warp (xor shuffles), then the NW warps in order
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      for (int o = G; o < 32; o <<= 1) {
+        s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], o);
+        s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], o);
+      }
+      if (slot == 0) {
+        red[(warp * 2 + 0) * nch + 4 * g + c] = s1[c];
+        red[(warp * 2 + 1) * nch + 4 * g + c] = s2[c];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * nch; i += NW * 32) {
+      const int which = i / nch, c = i - which * nch;
+      float s = 0.f;
+      for (int w = 0; w < NW; ++w) s += red[(w * 2 + which) * nch + c];
+      e.partial[(static_cast<int64_t>(cta) * 2 + which) * nch + c] = s;
+    }
   }
 }
 
@@ -286,7 +446,7 @@ __global__ void __launch_bounds__(NTHREADS, R == 1 ? 2 : 1) knn_small_kernel(con
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmallSmem<R>& sm = *reinterpret_cast<SmallSmem<R>*>(smem_raw);
   constexpr int KP = SmallSmem<R>::KP;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int b = blockIdx.y, q0 = blockIdx.x * TILE;
   const int N = a.N;
 

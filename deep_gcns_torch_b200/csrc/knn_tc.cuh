@@ -208,31 +208,47 @@ struct TcArgs {
   const float* xt;               // (B,N,C) node-major fp32 copy (exact re-rank)
   const float* sqmax;            // (B)
   int Cpad;
+  int wide;                      // consumer variant (cta_epilogue_wide)
+  int work_bytes;                // size of the work area, see tc_work_bytes
+  int flush_early, flush_late;   // packed path: buffered candidates per lane that trigger a flush (tiles 0-1 / later)
   int* fail_count;               // device counter
   int* fail_list;                // (B*N) encoded b*N + q
 };
 
-constexpr int TC_THREADS = 256;                       // two warpgroups, each thread r / r+128 owns query r
-constexpr int TC_FLUSH_AT = 9;                        // flush when any lane of the warp buffered this many
-constexpr int TC_BUF = 16;                            // >= TC_FLUSH_AT - 1 + 8 (checked every 8 columns)
-constexpr int TC_WORK_BYTES = 144 * 1024;              // >= 3 stages; sized for the post-streaming lists + staging
+constexpr int TC_THREADS = 128;                       // one warpgroup: thread r = TMEM lane r = query r
+constexpr int TC_FLUSH_AT = 9;                        // flush when any lane of the warp buffered this many (8-byte entries)
+constexpr int TC_BUF = 16;                            // 8-byte slots per thread, >= TC_FLUSH_AT - 1 + 8 (checked every 8 columns)
+constexpr int TC_FLUSH_EARLY = 10;                    // packed 4-byte entries: 32 slots; tight threshold while the
+constexpr int TC_FLUSH_LATE = 10;                     // list still moves a lot (first tiles), fuller batches afterwards
 constexpr int TC_STAGE_BYTES = TC_PLANES * 2 * TC_MAX_C * 128;   // 32 KB: planes x 2 MN blocks x 64 rows x 128 B
 
-struct TcSmem {
-  // `work`: operand area while streaming = [queries 48 KB | stage of warpgroup 0 | stage of warpgroup 1],
-  // all canonical MN-major SWIZZLE_128B: [plane][mn_block(2)][Cpad rows][128 B].  Afterwards the same
-  // 144 KB hold the two per-warpgroup candidate lists (front) and sel / staging buffers (back).
-  unsigned char work[TC_WORK_BYTES];
-  uint64_t cbuf[TC_BUF * TC_THREADS];               // 32 KB private candidate buffers, slot-major
-  float sqj[2][2][TILE];                            // [warpgroup][tile parity][column]
-  float cut[2][TILE];                               // approx key of each list's last entry (inf if not full)
-  float tau_pub[2][TILE];                           // each warpgroup's current admission threshold, read by the other
-  uint64_t mbar[2];
+// Shared memory of one CTA (128 queries of one cloud).  Several CTAs share an SM so that the
+// latency-bound phases of one (exact re-rank, neighbour gather) overlap the streaming phase of another.
+//   work (1024-aligned, work_bytes): while streaming [query planes 32 KB | candidate stage 32 KB], both
+//   canonical MN-major SWIZZLE_128B: [plane][mn_block(2)][Cpad rows][128 B]; afterwards
+//   [exact-sorted lists KP x 128 x 8 B | sel 128 x sel_ld x 4 B | consumer scratch].
+//   tail: the fixed-size part below.
+struct TcTail {
+  uint64_t cbuf[TC_BUF * TC_THREADS];               // 16 KB private candidate buffers, slot-major
+  float sqj[3][TILE];                               // [tile % 3][column]
+  uint64_t mbar;
   uint32_t tmem_base;
   unsigned char ok[TILE];
 };
 
-// 128 threads of one warpgroup copy one 128-point tile of the three planes into `dst`.
+// Bytes of the work area for list length KP, k kept neighbours and the chosen consumer.
+__host__ __device__ inline int tc_sel_ld(int k) { return k | 1; }
+__host__ __device__ inline size_t tc_work_bytes(int KP, int k, bool wide, int nch) {
+  size_t after = static_cast<size_t>(KP) * TILE * 8 + static_cast<size_t>(TILE) * tc_sel_ld(k) * 4;
+  after = (after + 15) & ~static_cast<size_t>(15);
+  if (wide) after += static_cast<size_t>(TC_THREADS / 32) * 2 * nch * 4;             // red
+  else after += 2 * static_cast<size_t>(32) * STAGE_LD * 4 + 2 * (TC_THREADS / 32) * 32 * 4 + 256;   // stage_max, stage_min, red
+  const size_t stream = 2 * static_cast<size_t>(TC_STAGE_BYTES);
+  const size_t w = after > stream ? after : stream;
+  return (w + 1023) & ~static_cast<size_t>(1023);
+}
+
+// 128 threads copy one 128-point tile of the planes into `dst`.
 // Thread r always moves 16-byte chunk (r & 15) of rows (r >> 4) + 8n: the swizzle term and all
 // offsets except the row / plane strides are loop invariant.
 __device__ __forceinline__ void tc_load_tile(unsigned char* dst, const __nv_bfloat16* planes_b, int Cpad, int N,
@@ -248,13 +264,6 @@ __device__ __forceinline__ void tc_load_tile(unsigned char* dst, const __nv_bflo
     unsigned char* dp = d + pl * (2 * Cpad * 128);
     for (int n = 0; n < groups; ++n) cp_async16(dp + n * 1024, sp + static_cast<int64_t>(n) * 8 * N);
   }
-}
-
-__device__ __forceinline__ void wg_barrier(int wg) {
-  asm volatile("bar.sync %0, %1;" ::"r"(1 + wg), "r"(TILE) : "memory");
-}
-__device__ __forceinline__ void gate_barrier() {     // both warpgroups, exactly once per thread
-  asm volatile("bar.sync 6, %0;" ::"r"(2 * TILE) : "memory");
 }
 
 // Branch-free insertion of (nk, nv) into the ascending register-resident list (k, v):
@@ -278,56 +287,68 @@ __device__ __forceinline__ void reg_insert(uint32_t (&k)[KP], uint32_t (&v)[KP],
 // lower the certificate's cut, never invalidate it.
 template <int KP>
 __device__ __forceinline__ void reg_insert_packed(uint32_t (&k)[KP], uint32_t nk) {
-  bool lt[KP];
+  // k[i] <- min(max(nk, k[i-1]), k[i]) with the OLD k[i-1]: two integer min/max per entry, no predicates
 #pragma unroll
-  for (int i = 0; i < KP; ++i) lt[i] = nk < k[i];
-#pragma unroll
-  for (int i = KP - 1; i > 0; --i) k[i] = lt[i - 1] ? k[i - 1] : (lt[i] ? nk : k[i]);
-  k[0] = lt[0] ? nk : k[0];
+  for (int i = KP - 1; i > 0; --i) k[i] = min(max(nk, k[i - 1]), k[i]);
+  k[0] = min(nk, k[0]);
 }
 
 template <int KP, bool PACKED>
-__global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
+__global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // SWIZZLE_128B atoms must sit on 1024-byte boundaries of the shared address space
-  unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_al);
+  unsigned char* work = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  TcTail& sm = *reinterpret_cast<TcTail*>(work + t.work_bytes);
   const KnnArgs& a = t.a;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int wg = tid >> 7, r = tid & (TILE - 1);        // warpgroup, query row = TMEM lane
+  const int r = tid;                                    // query row = TMEM lane
   const int b = blockIdx.y, q0 = blockIdx.x * TILE;
   const int N = a.N, Cpad = t.Cpad;
   const int plane_bytes = 2 * Cpad * 128;
   const __nv_bfloat16* planes_b = t.planes + static_cast<int64_t>(b) * TC_PLANES * Cpad * N;
   const float* sqb = a.sq + static_cast<int64_t>(b) * N;
-  unsigned char* qstage = sm.work;
-  unsigned char* mystage = sm.work + (1 + wg) * TC_STAGE_BYTES;
+  unsigned char* qstage = work;
+  unsigned char* stage = work + TC_STAGE_BYTES;
 
   if (tid == 0) {
-    mbar_init(&sm.mbar[0], 1);
-    mbar_init(&sm.mbar[1], 1);
+    mbar_init(&sm.mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(&sm.tmem_base, 256);
-  sm.tau_pub[wg][r] = INFINITY;
+  if (warp == 0) tmem_alloc(&sm.tmem_base, 256);     // two 128-column accumulators
   const int ntiles = N / TILE;
-  // queries (warpgroup 0 copies them) + each warpgroup's first candidate tile
-  if (wg == 0) tc_load_tile(qstage, planes_b, Cpad, N, q0, r);
-  if (wg < ntiles) {
-    tc_load_tile(mystage, planes_b, Cpad, N, wg * TILE, r);
-    sm.sqj[wg][0][r] = __ldg(sqb + wg * TILE + r);
-  }
+  tc_load_tile(qstage, planes_b, Cpad, N, q0, r);
+  tc_load_tile(stage, planes_b, Cpad, N, 0, r);
+  sm.sqj[0][r] = __ldg(sqb + r);
   cp_async_commit();
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  // One thread issues the 4 x Cpad/16 MMAs of a candidate tile into accumulator `buf` and commits.
+  auto issue_tile = [&](uint32_t tmem_acc) {
+    tc_fence_after();
+    const uint32_t abase = smem_u32(qstage), bbase = smem_u32(stage);
+    const int pa[4] = {0, 0, 1, 1};   // hi*hi, hi*mid, mid*hi, mid*mid
+    const int pb[4] = {0, 1, 0, 1};
+    uint32_t acc = 0;
+    for (int kk = 0; kk < Cpad / 16; ++kk) {
+#pragma unroll
+      for (int term = 0; term < 4; ++term) {
+        const uint64_t da = umma_desc_mn_sw128(abase + pa[term] * plane_bytes + kk * 2048, Cpad * 128, 1024);
+        const uint64_t db = umma_desc_mn_sw128(bbase + pb[term] * plane_bytes + kk * 2048, Cpad * 128, 1024);
+        umma_bf16(tmem_acc, da, db, kIdescBf16MnMn128x128, acc);
+        acc = 1;
+      }
+    }
+    umma_commit(&sm.mbar);
+  };
   cp_async_wait_all();
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = sm.tmem_base + static_cast<uint32_t>(wg * TILE);           // this warpgroup's accumulator
-  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t tmem = sm.tmem_base;
+  if (tid == 0) issue_tile(tmem);
 
   const int qg = q0 + r;
-  // the KP best approximate keys of THIS warpgroup's tiles, ascending, in registers
+  // the KP best approximate keys, ascending, in registers
   uint32_t lk[KP], lv[PACKED ? 1 : KP];
 #pragma unroll
   for (int i = 0; i < KP; ++i) {
@@ -335,25 +356,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
     if (!PACKED) lv[i] = 0xFFFFFFFFu;
   }
   const float sqq = __ldg(sqb + qg);
-  float tau_own = __uint_as_float(0x7FC00000u);   // NaN admits everything until the list is full
-  uint64_t* const cb0 = sm.cbuf + tid;            // private buffer: slots cb0[0], cb0[TC_THREADS], ...
-  const uint32_t cb_addr0 = smem_u32(cb0);
+  float tau_f = __uint_as_float(0x7FC00000u);     // NaN admits everything until the list is full
+  // private candidate buffer, slot-major: PACKED 32 slots x 4 B (key bits | 12-bit index), else 16 x 8 B
+  constexpr uint32_t ESZ = PACKED ? 4u : 8u;
+  const uint32_t cb_addr0 = smem_u32(sm.cbuf) + tid * ESZ;
   uint32_t cb_addr = cb_addr0;      // next free slot of the private buffer (shared-space byte address)
   // Warp-synchronous flush: every lane merges ITS buffered candidates in lockstep.
   auto flush = [&]() {
-    const int cnt = static_cast<int>((cb_addr - cb_addr0) / (TC_THREADS * 8u));
+    const int cnt = static_cast<int>((cb_addr - cb_addr0) / (TC_THREADS * ESZ));
     int mx = cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // buffer reads are volatile asm so that they stay ordered behind the filter's (volatile asm) stores
+    auto ld_entry32 = [&](int e) {
+      uint32_t v;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(cb_addr0 + static_cast<uint32_t>(e) * (TC_THREADS * 4u)));
+      return v;
+    };
+    auto ld_entry64 = [&](int e) {
+      uint64_t v;
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(cb_addr0 + static_cast<uint32_t>(e) * (TC_THREADS * 8u)));
+      return v;
+    };
+    uint32_t en_next = 0;
+    uint64_t kv_next = 0;
+    if (PACKED) en_next = ld_entry32(0); else kv_next = ld_entry64(0);   // slot 0 always exists
     for (int e = 0; e < mx; ++e) {
       uint32_t nk = 0xFFFFFFFFu, nv = 0u;
+      const uint32_t en = en_next;
+      const uint64_t kv = kv_next;
+      if (e + 1 < mx) {                 // prefetch the next round's entry behind this round's insertion
+        if (PACKED) en_next = ld_entry32(e + 1); else kv_next = ld_entry64(e + 1);
+      }
       if (e < cnt) {
-        const uint64_t kv = cb0[e * TC_THREADS];     // low word = index, high word = float key bits
-        nv = static_cast<uint32_t>(kv);
         if (PACKED) {
-          const float d2 = fmaxf(__uint_as_float(static_cast<uint32_t>(kv >> 32)) + sqq, 0.f);
-          nk = (__float_as_uint(d2) & 0xFFFFF000u) | (nv & 0xFFFu);
+          // entry = key bits with the low 12 mantissa bits replaced by the index; restore a LOWER bound of the key
+          const uint32_t kb = (en & 0x80000000u) ? (en | 0xFFFu) : (en & 0xFFFFF000u);
+          const float d2 = fmaxf(__uint_as_float(kb) + sqq, 0.f);
+          nk = (__float_as_uint(d2) & 0xFFFFF000u) | (en & 0xFFFu);
         } else {
+          nv = static_cast<uint32_t>(kv);              // low word = index, high word = float key bits
           nk = float_to_ordered(__uint_as_float(static_cast<uint32_t>(kv >> 32)));
         }
       }
@@ -364,124 +406,117 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
     }
     cb_addr = cb_addr0;
     if (PACKED) {   // admission in key units (distance minus |x_i|^2), one truncation step above the last entry
-      tau_own = lk[KP - 1] == 0xFFFFFFFFu ? __uint_as_float(0x7FC00000u)
-                                          : __uint_as_float((lk[KP - 1] & 0xFFFFF000u) + 0x1000u) - sqq;
+      tau_f = lk[KP - 1] == 0xFFFFFFFFu ? __uint_as_float(0x7FC00000u)
+                                        : __uint_as_float((lk[KP - 1] & 0xFFFFF000u) + 0x1000u) - sqq;
     } else {
-      tau_own = ordered_to_float(lk[KP - 1]);      // NaN while the list is not full
+      tau_f = ordered_to_float(lk[KP - 1]);        // NaN while the list is not full
     }
-    if (tau_own == tau_own) sm.tau_pub[wg][r] = tau_own;
   };
 
-  for (int tile = wg; tile < ntiles; tile += 2) {
-    const int par = (tile >> 1) & 1;
-    // operands of this tile have landed (own cp.async groups) -> visible to the tensor core
-    cp_async_wait_all();
-    fence_proxy_async();
-    tc_fence_before();
-    wg_barrier(wg);     // also: every thread of the warpgroup finished reading the accumulator of tile-2
-    if (r == 0) {
-      tc_fence_after();
-      const uint32_t abase = smem_u32(qstage), bbase = smem_u32(mystage);
-      const int pa[4] = {0, 0, 1, 1};   // hi*hi, hi*mid, mid*hi, mid*mid
-      const int pb[4] = {0, 1, 0, 1};
-      uint32_t acc = 0;
-      for (int kk = 0; kk < Cpad / 16; ++kk) {
-#pragma unroll
-        for (int term = 0; term < 4; ++term) {
-          const uint64_t da = umma_desc_mn_sw128(abase + pa[term] * plane_bytes + kk * 2048, Cpad * 128, 1024);
-          const uint64_t db = umma_desc_mn_sw128(bbase + pb[term] * plane_bytes + kk * 2048, Cpad * 128, 1024);
-          umma_bf16(tmem, da, db, kIdescBf16MnMn128x128, acc);
-          acc = 1;
-        }
-      }
-      umma_commit(&sm.mbar[wg]);
-    }
-    mbar_wait(&sm.mbar[wg], static_cast<uint32_t>(par));
+  // Pipeline per tile t: wait MMA(t) -> the stage is free: cp.async tile t+1 -> filter first half of
+  // accumulator t&1 -> (loads landed) barrier, issue MMA(t+1) into the other accumulator -> filter
+  // second half.  The only CTA barrier per tile also orders: every thread finished reading accumulator
+  // (t+1)&1 (tile t-1) and sqj[(t+2)%3] (tile t-1) before they are overwritten.
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int par = tile & 1;
+    const bool more = tile + 1 < ntiles;
+    const float sq_next = more ? __ldg(sqb + (tile + 1) * TILE + r) : 0.f;
+    mbar_wait(&sm.mbar, static_cast<uint32_t>(par));
     tc_fence_after();
-    // the stage is free again: prefetch this warpgroup's next tile behind the filter
-    if (tile + 2 < ntiles) {
-      tc_load_tile(mystage, planes_b, Cpad, N, (tile + 2) * TILE, r);
+    if (more) {
+      tc_load_tile(stage, planes_b, Cpad, N, (tile + 1) * TILE, r);
       cp_async_commit();
-      sm.sqj[wg][par ^ 1][r] = __ldg(sqb + (tile + 2) * TILE + r);
+      sm.sqj[(tile + 1) % 3][r] = sq_next;
     }
-    // Only warpgroup 0 pays for filling an empty list: warpgroup 1 holds its first filter until
-    // warpgroup 0 has published a threshold from its first tile.
-    if (wg == 1 && tile == 1) gate_barrier();
     // filter: thread = TMEM lane = query; approx key = |x_j|^2 - 2 x_i.x_j (row-constant |x_i|^2 omitted)
     const int j0 = tile * TILE;
-    const float4* sqj4 = reinterpret_cast<const float4*>(sm.sqj[wg][par]);
+    const float4* sqj4 = reinterpret_cast<const float4*>(sm.sqj[tile % 3]);
     const bool diag = a.exclude_self && j0 == q0;
-    // Admission threshold: min of both warpgroups' thresholds.  Each is >= the final KP-th best
-    // approximate key over ALL candidates, so rejecting key >= min cannot lose a top-KP candidate
-    // and "every unlisted candidate has key >= min(final thresholds)" still holds for the certificate.
-    float tau_f = tau_own;
-    {
-      const float other = sm.tau_pub[wg ^ 1][r];
-      if (!(tau_f < other)) tau_f = (tau_f == tau_f) ? fminf(tau_f, other) : other;
-      if (tau_f == INFINITY) tau_f = __uint_as_float(0x7FC00000u);
-    }
+    const uint32_t tacc = tmem + static_cast<uint32_t>(par * TILE) + lane_base;
+    const uint32_t flush_bytes = PACKED ? (tile < 2 ? t.flush_early : t.flush_late) * TC_THREADS * 4u
+                                        : TC_FLUSH_AT * TC_THREADS * 8u;
 #pragma unroll 1
     for (int cchunk = 0; cchunk < TILE / 32; ++cchunk) {
+      if (cchunk == 2 && more) {
+        cp_async_wait_all();
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) issue_tile(tmem + static_cast<uint32_t>((par ^ 1) * TILE));
+      }
       float v[32];
       __syncwarp();   // tcgen05.ld is warp-collective
-      tmem_ld32(tmem + lane_base + static_cast<uint32_t>(cchunk * 32), v);
+      tmem_ld32(tacc + static_cast<uint32_t>(cchunk * 32), v);
       if (diag && (r >> 5) == cchunk) {   // self exclusion: only in the diagonal tile, only one column
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (i == (r & 31)) v[i] = -INFINITY;   // key becomes +inf
       }
+      // PACKED: one LOP3 builds the entry (key & R & I) | (R ^ I) with R = ~0xFFF | index bits 5..11
+      // (tile, chunk) and the immediate I = ~0xFFF | index bits 0..4
+      const uint32_t rbits = 0xFFFFF000u | static_cast<uint32_t>(j0 + cchunk * 32);
+      // |x_j|^2 of the next 8 columns is fetched before this group's buffer stores (shared-memory
+      // loads cannot be hoisted over stores by the assembler)
+      float4 n0 = sqj4[cchunk * 8], n1 = sqj4[cchunk * 8 + 1];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const float4 s0 = sqj4[cchunk * 8 + g * 2], s1 = sqj4[cchunk * 8 + g * 2 + 1];
+        const float4 s0 = n0, s1 = n1;
+        if (g < 3) {
+          n0 = sqj4[cchunk * 8 + g * 2 + 2];
+          n1 = sqj4[cchunk * 8 + g * 2 + 3];
+        }
         const float sq8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         uint32_t jcur = static_cast<uint32_t>(j0 + cchunk * 32 + g * 8);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float key = fmaf(-2.0f, v[g * 8 + i], sq8[i]);
-          // if (!(key > tau)) { buffer[slot] = (key, index); ++slot; }  - predicated, no branch
-          asm volatile(
-              "{\n"
-              ".reg .pred p;\n"
-              "setp.leu.f32 p, %1, %3;\n"
-              "@p st.shared.v2.b32 [%0], {%2, %1};\n"
-              "@p add.u32 %0, %0, %4;\n"
-              "}"
-              : "+r"(cb_addr)
-              : "f"(key), "r"(jcur), "f"(tau_f), "n"(TC_THREADS * 8)
-              : "memory");
-          ++jcur;
+          // if (!(key > tau)) { buffer[slot] = entry; ++slot; }  - predicated, no branch
+          if (PACKED) {
+            const uint32_t ibits = 0xFFFFF000u | static_cast<uint32_t>(g * 8 + i);
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                ".reg .b32 en;\n"
+                "lop3.b32 en, %1, %2, %5, 0xE6;\n"          // (a & b & c) | (b ^ c)
+                "setp.leu.f32 p, %1, %3;\n"
+                "@p st.shared.b32 [%0], en;\n"
+                "@p add.u32 %0, %0, %4;\n"
+                "}"
+                : "+r"(cb_addr)
+                : "r"(__float_as_uint(key)), "r"(rbits), "f"(tau_f), "n"(TC_THREADS * 4), "r"(ibits));
+          } else {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "setp.leu.f32 p, %1, %3;\n"
+                "@p st.shared.v2.b32 [%0], {%2, %1};\n"
+                "@p add.u32 %0, %0, %4;\n"
+                "}"
+                : "+r"(cb_addr)
+                : "f"(key), "r"(jcur), "f"(tau_f), "n"(TC_THREADS * 8));
+            ++jcur;
+          }
         }
-        if (__any_sync(0xffffffffu, cb_addr - cb_addr0 >= TC_FLUSH_AT * TC_THREADS * 8u)) {
-          flush();
-          const float other = sm.tau_pub[wg ^ 1][r];
-          tau_f = tau_own;
-          if (!(tau_f < other)) tau_f = (tau_f == tau_f) ? fminf(tau_f, other) : other;
-          if (tau_f == INFINITY) tau_f = __uint_as_float(0x7FC00000u);
-        }
+        if (__any_sync(0xffffffffu, cb_addr - cb_addr0 >= flush_bytes)) flush();
       }
     }
-    if (wg == 0 && tile == 0) {   // publish after the first tile and open the gate
-      flush();
-      gate_barrier();
-    }
   }
-  if (wg == 1 && ntiles < 2) gate_barrier();   // arrive once even without a tile
   flush();
   tc_fence_before();
   __syncthreads();   // every MMA has completed, nobody touches operands or TMEM any more
   if (warp == 0) tmem_dealloc(sm.tmem_base, 256);
 
-  // ---- per list: exact re-rank of the listed candidates (fp32 FMA chain, k ascending) --------------
-  uint64_t* list = reinterpret_cast<uint64_t*>(sm.work) + static_cast<size_t>(wg) * KP * TILE;   // [KP][TILE]
+  // ---- exact re-rank of the listed candidates (fp32 FMA chain, k ascending) --------------------------
+  uint64_t* list = reinterpret_cast<uint64_t*>(work);   // [KP][TILE]
   // lower bound of every unlisted candidate's approximate key (PACKED: of its squared distance)
-  sm.cut[wg][r] = (lk[KP - 1] == 0xFFFFFFFFu) ? INFINITY
-                  : (PACKED ? __uint_as_float(lk[KP - 1] & 0xFFFFF000u) : ordered_to_float(lk[KP - 1]));
+  const float cut = (lk[KP - 1] == 0xFFFFFFFFu) ? INFINITY
+                    : (PACKED ? __uint_as_float(lk[KP - 1] & 0xFFFFF000u) : ordered_to_float(lk[KP - 1]));
   const int C = a.C;
   const float* xtb = t.xt + static_cast<int64_t>(b) * N * C;
-  float xq[TC_MAX_C];
-#pragma unroll
-  for (int c = 0; c < TC_MAX_C; ++c) xq[c] = c < C ? __ldg(xtb + static_cast<int64_t>(qg) * C + c) : 0.f;
   {
+    float xq[TC_MAX_C];
+#pragma unroll
+    for (int c = 0; c < TC_MAX_C; ++c) xq[c] = c < C ? __ldg(xtb + static_cast<int64_t>(qg) * C + c) : 0.f;
     // pass 1: exact distances of all listed candidates - pure loads + FMA chains, no shared-memory
     // traffic in between, so the loads of the next candidates overlap the chains of the current one
     float dex[KP];
@@ -530,33 +565,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
     }
     for (int i = e; i < KP; ++i) list[i * TILE + r] = KEY_MAX;
   }
-  __syncthreads();
-  // ---- merge the two exact-sorted lists, certify (warpgroup 0, thread = query) -----------------------------
-  uint64_t* la = reinterpret_cast<uint64_t*>(sm.work);
-  uint64_t* lb = la + static_cast<size_t>(KP) * TILE;
-  if (wg == 0) {
-    const int K = a.K;
-    int na = 0, nb = 0;
-    for (int o = 0; o < K; ++o) {          // how many of the K winners come from each list
-      const uint64_t ka = na < KP ? la[na * TILE + r] : KEY_MAX;
-      const uint64_t kb = nb < KP ? lb[nb * TILE + r] : KEY_MAX;
-      if (ka <= kb) ++na; else ++nb;
-    }
-    int ia = na - 1, ib = nb - 1;
-    for (int o = K - 1; o >= 0; --o) {     // in-place merge from the back: o >= ia always
-      const uint64_t ka = ia >= 0 ? la[ia * TILE + r] : 0ull;
-      const uint64_t kb = ib >= 0 ? lb[ib * TILE + r] : 0ull;
-      if (ib < 0 || (ia >= 0 && ka > kb)) {
-        la[o * TILE + r] = ka;
-        --ia;
-      } else {
-        la[o * TILE + r] = kb;
-        --ib;
-      }
-    }
-    const uint64_t kth = la[(K - 1) * TILE + r];
+  // ---- certificate (thread = query) ------------------------------------------------------------------
+  {
+    const uint64_t kth = list[(a.K - 1) * TILE + r];
     bool ok = kth != KEY_MAX;
-    const float cut = fminf(sm.cut[0][r], sm.cut[1][r]);       // every unlisted candidate has approx key >= cut
     if (ok && cut < INFINITY) {
       const float dk = ordered_to_float(static_cast<uint32_t>(kth >> 32));
       const float smax = __ldg(t.sqmax + b);
@@ -573,39 +585,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcArgs t) {
     }
   }
   __syncthreads();
-  // ---- consumer: sel / staging live at the back of the work area (lists occupy < 78 KB of the front) --------
-  int* sel = reinterpret_cast<int*>(sm.work + TC_WORK_BYTES - 66 * 1024);
-  float* stage_max = reinterpret_cast<float*>(sm.work + TC_WORK_BYTES - 34 * 1024);
-  float* stage_min = stage_max + 32 * STAGE_LD + 32;
-  cta_epilogue<TC_THREADS / 32>(a, b, q0, la, sm.ok, sel, stage_max, stage_min, blockIdx.y * gridDim.x + blockIdx.x);
+  // ---- consumer: sel and scratch follow the lists in the work area ---------------------------------------
+  const int sel_ld = tc_sel_ld(a.k);
+  int* sel = reinterpret_cast<int*>(work + static_cast<size_t>(KP) * TILE * 8);
+  float* scratch = reinterpret_cast<float*>(
+      work + ((static_cast<size_t>(KP) * TILE * 8 + static_cast<size_t>(TILE) * sel_ld * 4 + 15) & ~static_cast<size_t>(15)));
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  if (t.wide) {
+    if (a.epi.mode == EPI_EDGE && a.epi.norm == DGCN_NORM_BATCH_TRAIN)
+      cta_epilogue_wide<TC_THREADS / 32, true>(a, b, q0, list, sm.ok, sel, sel_ld, scratch, cta);
+    else
+      cta_epilogue_wide<TC_THREADS / 32, false>(a, b, q0, list, sm.ok, sel, sel_ld, scratch, cta);
+  } else {
+    float* stage_max = scratch;
+    float* stage_min = stage_max + 32 * STAGE_LD + 32;
+    cta_epilogue<TC_THREADS / 32>(a, b, q0, list, sm.ok, sel, stage_max, stage_min, cta, sel_ld);
+  }
 }
 
 // ---- exact completion of uncertified queries ------------------------------------------------------------
-// One warp per failed query: exact fp32 distances to all N candidates (lanes over candidates,
-// FMA chain over channels), warp-wide sorted list of the best 64, then the per-query consumer.
+// One CTA per failed query: the 8 warps split the N candidates (lanes over candidates, exact fp32 FMA
+// chain over channels, the query's channels broadcast from shared memory), each keeps a warp-wide
+// sorted list of its best 64, the 8 lists are merged by one bitonic sort in shared memory, then warp 0
+// runs the per-query consumer.  A lone uncertified query therefore costs ~N/256 candidate rounds, not N/32.
 __global__ void __launch_bounds__(256) knn_exact_rows_kernel(const KnnArgs a, const int* __restrict__ fail_count,
                                                             const int* __restrict__ fail_list,
                                                             float* __restrict__ partial_extra) {
-  __shared__ int sel_all[8][64];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nwarps = gridDim.x * 8;
+  __shared__ float xq[TC_MAX_C];
+  __shared__ uint64_t merged[8 * 64];
+  __shared__ int sel[64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int total = *fail_count;
   const Epilogue& e = a.epi;
-  const int N = a.N, C = a.C, K = a.K, k = a.k;
+  const int N = a.N, C = a.C, k = a.k;
   float s1acc[4] = {0.f, 0.f, 0.f, 0.f}, s2acc[4] = {0.f, 0.f, 0.f, 0.f};   // c_out <= 128 covered per lane
-  for (int f = blockIdx.x * 8 + warp; f < total; f += nwarps) {
+  for (int f = blockIdx.x; f < total; f += gridDim.x) {
     const int code = fail_list[f];
     const int b = code / N, q = code % N;
     const float* xb = a.x + b * a.sb;
     const float* sqb = a.sq + static_cast<int64_t>(b) * N;
     const float sqq = sqb[q];
-    uint64_t r0 = KEY_MAX, r1 = KEY_MAX;   // sorted 64-entry list: r0 = ranks 0..31, r1 = 32..63
-    for (int j0 = 0; j0 < N; j0 += 32) {
+    __syncthreads();                       // the previous query's xq / merged / sel are no longer read
+    if (tid < C) xq[tid] = __ldg(xb + tid * a.sc + q);
+    __syncthreads();
+    uint64_t r0 = KEY_MAX, r1 = KEY_MAX;   // this warp's sorted 64-entry list: r0 = ranks 0..31, r1 = 32..63
+    for (int j0 = warp * 32; j0 < N; j0 += 256) {
       const int j = j0 + lane;
       uint64_t key = KEY_MAX;
       if (j < N && !(a.exclude_self && j == q)) {
+        const float* xj = xb + j;
         float acc = 0.f;
-        for (int c = 0; c < C; ++c) acc = fmaf(__ldg(xb + c * a.sc + q), __ldg(xb + c * a.sc + j), acc);
+#pragma unroll 8
+        for (int c = 0; c < C; ++c) acc = fmaf(xq[c], __ldg(xj + c * a.sc), acc);
         key = make_key((sqq + (-2.0f * acc)) + sqb[j], static_cast<uint32_t>(j));
       }
       const uint64_t worst = shfl_u64(r1, 31);
@@ -630,19 +661,15 @@ __global__ void __launch_bounds__(256) knn_exact_rows_kernel(const KnnArgs a, co
         }
       }
     }
-    (void)K;
-    int* sel = sel_all[warp];
+    merged[warp * 64 + lane] = r0;
+    merged[warp * 64 + 32 + lane] = r1;
+    __syncthreads();
+    if (warp != 0) continue;               // (the loop-top barrier keeps the CTA together)
+    warp_bitonic_sort(merged, 512, lane);
     const int64_t node0 = static_cast<int64_t>(b) * N;
-    __syncwarp();
-    // ranks are warp-distributed: broadcast them one by one (k <= 64)
-    for (int l = 0; l < k; ++l) {
-      const int rank = keep_rank(a, l);
-      const uint64_t key = (rank < 32) ? shfl_u64(r0, rank) : shfl_u64(r1, rank - 32);
-      if (lane == 0) sel[l] = static_cast<int>(static_cast<uint32_t>(key));
-    }
-    __syncwarp();
     for (int l = lane; l < k; l += 32) {
-      const int idx = sel[l];
+      const int idx = static_cast<int>(static_cast<uint32_t>(merged[keep_rank(a, l)]));
+      sel[l] = idx;
       const int64_t o = (node0 + q) * k + l;
       if (e.nbr) e.nbr[o] = idx;
       if (e.edge_index) {
@@ -650,6 +677,7 @@ __global__ void __launch_bounds__(256) knn_exact_rows_kernel(const KnnArgs a, co
         e.edge_index[static_cast<int64_t>(a.B) * N * k + o] = q;
       }
     }
+    __syncwarp();
     if (e.mode == EPI_EDGE) {
       const float slope = epi_slope(e);
       const bool train = e.norm == DGCN_NORM_BATCH_TRAIN;
@@ -681,9 +709,9 @@ __global__ void __launch_bounds__(256) knn_exact_rows_kernel(const KnnArgs a, co
     }
     __syncwarp();
   }
-  // train-mode statistics of the queries completed here: one extra partial row per warp
-  if (e.mode == EPI_EDGE && e.norm == DGCN_NORM_BATCH_TRAIN && partial_extra) {
-    const int64_t rowi = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  // train-mode statistics of the queries completed here: one extra partial row per CTA (warp 0 holds them)
+  if (warp == 0 && e.mode == EPI_EDGE && e.norm == DGCN_NORM_BATCH_TRAIN && partial_extra) {
+    const int64_t rowi = blockIdx.x;
     for (int u = 0; u < 4; ++u) {
       const int c = u * 32 + lane;
       if (c < e.c_out) {
