@@ -79,6 +79,7 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
   t.a = a;
   t.planes = planes;
   t.xt = xt;
+  t.xt32 = (reinterpret_cast<uintptr_t>(xt) & 31) == 0 ? 1 : 0;
   t.sqmax = sqmax;
   t.Cpad = cpad;
   t.fail_count = fail;

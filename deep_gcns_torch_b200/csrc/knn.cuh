@@ -86,6 +86,29 @@ __device__ __forceinline__ void edge_query(const Epilogue& e, int64_t node0, int
   const float p = __ldg(e.pq + (node0 + q) * ld + c);
   const float* qbase = e.pq + node0 * ld + e.c_out + c;
   int l = 0;
+  if (e.norm != DGCN_NORM_BATCH_TRAIN && slope >= 0.f) {
+    // no statistics needed and act is non-decreasing, like the rounded p + q: max / min commute with
+    // them bit for bit, so reduce the raw gathered values and activate once
+    float rmax = -INFINITY, rmin = INFINITY;
+    for (; l + 8 <= k; l += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(qbase + static_cast<int64_t>(sel[l + u]) * ld);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        rmax = fmaxf(rmax, v[u]);
+        rmin = fminf(rmin, v[u]);
+      }
+    }
+    for (; l < k; ++l) {
+      const float v = __ldg(qbase + static_cast<int64_t>(sel[l]) * ld);
+      rmax = fmaxf(rmax, v);
+      rmin = fminf(rmin, v);
+    }
+    vmax = act_apply(p + rmax, slope);
+    vmin = act_apply(p + rmin, slope);
+    return;
+  }
   for (; l + 8 <= k; l += 8) {   // eight independent row reads in flight per lane
     float v[8];
 #pragma unroll
@@ -301,6 +324,9 @@ __device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q
   }
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   float* dst = edge ? e.out : e.r_out;
+  // eval with a non-decreasing activation (or MRConv's plain max): reduce the raw gathered values
+  const bool mono = !TRAIN && (!edge || slope >= 0.f);
+  const bool need_min = edge && __any_sync(0xffffffffu, bs[0] < 0.f || bs[1] < 0.f || bs[2] < 0.f || bs[3] < 0.f);
   for (int round = 0; round < per_slot; round += 8) {
     const int qlb = warp * QPW + slot * per_slot + round;    // first of eight consecutive queries
     float res[8][4], res2[TRAIN ? 8 : 1][4];
@@ -323,22 +349,44 @@ __device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q
             const int idx = srow[min(l0 + u, k - 1)];
             v[u] = __ldg(reinterpret_cast<const float4*>(rows + static_cast<int64_t>(idx) * ld));
           }
+          if (mono) {
+            // act is non-decreasing (slope >= 0) and so is the rounded p + q: max / min commute with them,
+            // bit for bit - one FMNMX per gathered element (tail duplicates are harmless)
 #pragma unroll
-          for (int u = 0; u < 10; ++u) {
-            if (l0 + u < k) {
+            for (int u = 0; u < 10; ++u) {
               const float w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-              const float pp[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const float av = edge ? act_apply(pp[c] + w[c], slope) : w[c];
-                vmax[c] = fmaxf(vmax[c], av);
-                if (edge) vmin[c] = fminf(vmin[c], av);
-                if (TRAIN) {
-                  s1[c] += av;
-                  s2[c] = fmaf(av, av, s2[c]);
+                vmax[c] = fmaxf(vmax[c], w[c]);
+                if (need_min) vmin[c] = fminf(vmin[c], w[c]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 10; ++u) {
+              if (l0 + u < k) {
+                const float w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                const float pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const float av = act_apply(pp[c] + w[c], slope);
+                  vmax[c] = fmaxf(vmax[c], av);
+                  vmin[c] = fminf(vmin[c], av);
+                  if (TRAIN) {
+                    s1[c] += av;
+                    s2[c] = fmaf(av, av, s2[c]);
+                  }
                 }
               }
             }
+          }
+        }
+        if (mono && edge) {
+          const float pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            vmax[c] = act_apply(pp[c] + vmax[c], slope);
+            vmin[c] = act_apply(pp[c] + vmin[c], slope);
           }
         }
       }

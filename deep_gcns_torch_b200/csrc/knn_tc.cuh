@@ -202,6 +202,13 @@ __global__ void sqmax_kernel(const float* __restrict__ sq, int N, float* __restr
 }
 
 // ---- the tensor-core kernel ------------------------------------------------------------------------
+// 256-bit read-only global load (sm_100: LDG.E.256); p must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const float* p, float (&w)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3]), "=f"(w[4]), "=f"(w[5]), "=f"(w[6]), "=f"(w[7])
+               : "l"(p));
+}
+
 struct TcArgs {
   KnnArgs a;
   const __nv_bfloat16* planes;   // (B,3,Cpad,N)
@@ -210,6 +217,7 @@ struct TcArgs {
   int Cpad;
   int wide;                      // consumer variant (cta_epilogue_wide)
   int work_bytes;                // size of the work area, see tc_work_bytes
+  int xt32;                      // xt is 32-byte aligned: 256-bit row loads in the exact re-rank
   int flush_early, flush_late;   // packed path: buffered candidates per lane that trigger a flush (tiles 0-1 / later)
   int* fail_count;               // device counter
   int* fail_list;                // (B*N) encoded b*N + q
@@ -526,7 +534,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
       const int j = valid ? static_cast<int>(PACKED ? (lk[u] & 0xFFFu) : lv[u]) : qg;
       const float* xj = xtb + static_cast<int64_t>(j) * C;
       float acc = 0.f;
-      if ((C & 3) == 0) {
+      if ((C & 7) == 0 && t.xt32) {
+        // one 256-bit load per 8 channels: each lane reads a different row, so every load is its own
+        // L1 wavefront - half as many as with 128-bit loads
+#pragma unroll
+        for (int c = 0; c < TC_MAX_C; c += 8) {
+          if (c < C) {
+            float w[8];
+            ldg256(xj + c, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc = fmaf(xq[c + i], w[i], acc);
+          }
+        }
+      } else if ((C & 3) == 0) {
 #pragma unroll
         for (int c = 0; c < TC_MAX_C; c += 4) {
           if (c < C) {
