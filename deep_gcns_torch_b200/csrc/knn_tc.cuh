@@ -39,6 +39,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {     // release semantics at CTA scope
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // bounded spin: a tensor-core pipeline that never signals must trap, not hang the GPU
   for (uint32_t spin = 0;; ++spin) {
@@ -239,7 +242,8 @@ constexpr int TC_STAGE_BYTES = TC_PLANES * 2 * TC_MAX_C * 128;   // 32 KB: plane
 struct TcTail {
   uint64_t cbuf[TC_BUF * TC_THREADS];               // 16 KB private candidate buffers, slot-major
   float sqj[3][TILE];                               // [tile % 3][column]
-  uint64_t mbar;
+  uint64_t mbar;                                    // MMA of a tile has completed (tcgen05.commit)
+  uint64_t mbar_ready;                              // all 128 threads: next tile's operands landed, other accumulator drained
   uint32_t tmem_base;
   unsigned char ok[TILE];
 };
@@ -320,6 +324,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
 
   if (tid == 0) {
     mbar_init(&sm.mbar, 1);
+    mbar_init(&sm.mbar_ready, TC_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, 256);     // two 128-column accumulators
@@ -446,11 +451,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
 #pragma unroll 1
     for (int cchunk = 0; cchunk < TILE / 32; ++cchunk) {
       if (cchunk == 2 && more) {
+        // split barrier: everybody arrives (own loads landed and fenced, own reads of the other
+        // accumulator retired), only the issuing thread waits for the full count
         cp_async_wait_all();
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) issue_tile(tmem + static_cast<uint32_t>((par ^ 1) * TILE));
+        mbar_arrive(&sm.mbar_ready);
+        if (tid == 0) {
+          mbar_wait(&sm.mbar_ready, static_cast<uint32_t>(par));
+          issue_tile(tmem + static_cast<uint32_t>((par ^ 1) * TILE));
+        }
       }
       float v[32];
       __syncwarp();   // tcgen05.ld is warp-collective
