@@ -175,7 +175,7 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
   int cap = next_pow2(static_cast<int>(expect > 2 * K ? expect : 2 * K));
   if (cap > 2048) cap = 2048;
   const bool fast = N >= 512 && cap >= K;
-  const size_t per_warp_f = static_cast<size_t>(cap) * 8 + static_cast<size_t>((a.k + 31) / 32 * 32) * 4;
+  const size_t per_warp_f = static_cast<size_t>(cap) * 8 + static_cast<size_t>((a.k + 31) / 32 * 32) * 4 + 2560;   // keys, sel, multi-select tables (hist 256, prefix 260 ints, 256 marks -> 2320 B)
   int warps_f = static_cast<int>((100u << 10) / per_warp_f);
   if (warps_f > 8) warps_f = 8;
   if (warps_f < 1) warps_f = 1;

@@ -648,12 +648,13 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t* s, int n, int lane) 
 
 // Per-row consumer shared by the slab kernels: sk holds the row's sorted keys (ascending), sel is a
 // k-entry scratch.  Writes the selected neighbour ids and runs the fused EdgeConv / MRConv consumer.
+// sk == nullptr: sel already holds the k selected neighbour ids.
 __device__ __forceinline__ void row_consume(const KnnArgs& a, int b, int q, const uint64_t* sk, int* sel, int lane) {
   const int N = a.N, k = a.k;
   const Epilogue& e = a.epi;
   const int64_t node0 = static_cast<int64_t>(b) * N;
   for (int l = lane; l < k; l += 32) {
-    int idx = static_cast<int>(static_cast<uint32_t>(sk[keep_rank(a, l)]));
+    int idx = sk ? static_cast<int>(static_cast<uint32_t>(sk[keep_rank(a, l)])) : sel[l];
     sel[l] = idx;
     int64_t o = (node0 + q) * k + l;
     if (e.nbr) e.nbr[o] = idx;
@@ -806,7 +807,7 @@ __global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const f
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = a.N, K = a.K, k = a.k;
-  const size_t per_warp = static_cast<size_t>(CAP) * 8 + static_cast<size_t>((k + 31) / 32 * 32) * 4;
+  const size_t per_warp = static_cast<size_t>(CAP) * 8 + static_cast<size_t>((k + 31) / 32 * 32) * 4 + 2560;
   unsigned char* mine = smem_raw + per_warp * warp;
   uint64_t* sk = reinterpret_cast<uint64_t*>(mine);
   int* sel = reinterpret_cast<int*>(mine + static_cast<size_t>(CAP) * 8);
@@ -876,12 +877,120 @@ __global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const f
     if (lane == 0) row_list[atomicAdd(row_count, 1)] = static_cast<int>(row);
     return;
   }
-  int KP = 128;
-  while (KP < w) KP <<= 1;
-  for (int i = w + lane; i < KP; i += 32) sk[i] = KEY_MAX;
+  if (k > 64) {   // many kept ranks: plain sort of everything below the bound
+    int KP = 128;
+    while (KP < w) KP <<= 1;
+    for (int i = w + lane; i < KP; i += 32) sk[i] = KEY_MAX;
+    __syncwarp();
+    warp_bitonic_sort(sk, KP, lane);
+    row_consume(a, b, q, sk, sel, lane);
+    return;
+  }
+  // 3. multi-select: only the k ranks keep_rank(l) of the K smallest are wanted (dilation keeps every d-th).
+  //    Histogram the w compacted keys over 256 distance bins between the smallest sample and the bound,
+  //    find the bins holding wanted ranks, compact those bins' keys in place, sort only them.
+  int* hist = sel + (k + 31) / 32 * 32;       // [256] keys per bin, then reused: keys in UNMARKED bins below
+  int* pre = hist + 256;                      // [257] exclusive prefix of hist
+  unsigned char* mark = reinterpret_cast<unsigned char*>(pre + 260);   // [256]
+  const float dlo = ordered_to_float(__shfl_sync(0xffffffffu, smp[0], 0));
+  const float dhi = ordered_to_float(__shfl_sync(0xffffffffu, rank < 32 ? smp[0] : rank < 64 ? smp[1] : rank < 96 ? smp[2] : smp[3], rank & 31));
+  const float scale = dhi > dlo ? 255.99f / (dhi - dlo) : 0.f;
+  auto bin_of = [&](uint64_t key) {
+    const float d = ordered_to_float(static_cast<uint32_t>(key >> 32));
+    const float t = (d - dlo) * scale;                 // monotone in d; NaN / negative -> bin 0
+    return t > 0.f ? min(255, static_cast<int>(t)) : 0;
+  };
+  for (int i = lane; i < 256; i += 32) {
+    hist[i] = 0;
+    mark[i] = 0;
+  }
   __syncwarp();
-  warp_bitonic_sort(sk, KP, lane);
-  row_consume(a, b, q, sk, sel, lane);
+  for (int i = lane; i < w; i += 32) atomicAdd(&hist[bin_of(sk[i])], 1);
+  __syncwarp();
+  {   // exclusive prefix: lane owns bins [8 lane, 8 lane + 8)
+    int loc[8], sum = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      loc[u] = sum;
+      sum += hist[lane * 8 + u];
+    }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const int base = inc - sum;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) pre[lane * 8 + u] = base + loc[u];
+    if (lane == 31) pre[256] = inc;
+  }
+  __syncwarp();
+  // bin of every wanted rank (binary search: last b with pre[b] <= r)
+  int mybin[2] = {0, 0};
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int l = lane + 32 * j;
+    if (l < k) {
+      const int r = keep_rank(a, l);
+      int lo = 0, hi = 256;            // pre[lo] <= r < pre[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pre[mid] <= r) lo = mid; else hi = mid;
+      }
+      mybin[j] = lo;
+      mark[lo] = 1;
+    }
+  }
+  __syncwarp();
+  {   // hist <- number of keys in unmarked bins below b (exclusive prefix over unmarked bins)
+    int loc[8], sum = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      loc[u] = sum;
+      sum += mark[lane * 8 + u] ? 0 : hist[lane * 8 + u];
+    }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const int base = inc - sum;
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) hist[lane * 8 + u] = base + loc[u];
+  }
+  __syncwarp();
+  // in-place compaction of the keys of marked bins (write position never passes the read position)
+  int T = 0;
+  for (int i0 = 0; i0 < w; i0 += 32) {
+    const int i = i0 + lane;
+    uint64_t key = KEY_MAX;
+    bool take = false;
+    if (i < w) {
+      key = sk[i];
+      take = mark[bin_of(key)] != 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    __syncwarp();
+    if (take) sk[T + __popc(m & ((1u << lane) - 1u))] = key;
+    T += __popc(m);
+  }
+  int TP = 32;
+  while (TP < T) TP <<= 1;
+  __syncwarp();
+  for (int i = T + lane; i < TP; i += 32) sk[i] = KEY_MAX;
+  __syncwarp();
+  warp_bitonic_sort(sk, TP, lane);
+  // rank r sits at position r - (#keys in unmarked bins below its bin) of the sorted marked keys
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int l = lane + 32 * j;
+    if (l < k) sel[l] = static_cast<int>(static_cast<uint32_t>(sk[keep_rank(a, l) - hist[mybin[j]]]));
+  }
+  __syncwarp();
+  row_consume(a, b, q, nullptr, sel, lane);
 }
 
 }  // namespace dgcn

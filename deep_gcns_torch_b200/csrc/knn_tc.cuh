@@ -39,8 +39,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {     // release semantics at CTA scope
-  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+// Arrive (release) and report whether this arrival - or one that raced with it - completed the phase.
+__device__ __forceinline__ bool mbar_arrive_completes(uint64_t* bar) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .b64 st;\n"
+      ".reg .pred P1;\n"
+      "mbarrier.arrive.shared::cta.b64 st, [%1];\n"
+      "mbarrier.test_wait.shared::cta.b64 P1, [%1], st;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(done)
+      : "r"(smem_u32(bar))
+      : "memory");
+  return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // bounded spin: a tensor-core pipeline that never signals must trap, not hang the GPU
@@ -245,6 +258,7 @@ struct TcTail {
   uint64_t mbar;                                    // MMA of a tile has completed (tcgen05.commit)
   uint64_t mbar_ready;                              // all 128 threads: next tile's operands landed, other accumulator drained
   uint32_t tmem_base;
+  int issue_ticket;                                 // next tile whose MMAs have not been issued yet
   unsigned char ok[TILE];
 };
 
@@ -325,6 +339,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
   if (tid == 0) {
     mbar_init(&sm.mbar, 1);
     mbar_init(&sm.mbar_ready, TC_THREADS);
+    sm.issue_ticket = 1;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, 256);     // two 128-column accumulators
@@ -452,14 +467,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
     for (int cchunk = 0; cchunk < TILE / 32; ++cchunk) {
       if (cchunk == 2 && more) {
         // split barrier: everybody arrives (own loads landed and fenced, own reads of the other
-        // accumulator retired), only the issuing thread waits for the full count
+        // accumulator retired)
         cp_async_wait_all();
         fence_proxy_async();
         tc_fence_before();
-        mbar_arrive(&sm.mbar_ready);
-        if (tid == 0) {
-          mbar_wait(&sm.mbar_ready, static_cast<uint32_t>(par));
-          issue_tile(tmem + static_cast<uint32_t>((par ^ 1) * TILE));
+        // whoever arrives last sees the phase complete and issues (the ticket settles races): nobody waits
+        if (mbar_arrive_completes(&sm.mbar_ready)) {
+          if (atomicCAS(&sm.issue_ticket, tile + 1, tile + 2) == tile + 1)
+            issue_tile(tmem + static_cast<uint32_t>((par ^ 1) * TILE));
         }
       }
       float v[32];

@@ -268,6 +268,59 @@ def test_tensor_core_prefilter_equals_exact_fp32_path(shape):
         _native.set_knn_path("auto")
 
 
+@pytest.mark.parametrize("cfg", [
+    # C, c_out, N, k, d, conv, act
+    (32, 32, 256, 9, 1, "edge", "relu"),
+    (64, 64, 512, 20, 2, "edge", "leakyrelu"),
+    (16, 128, 384, 16, 1, "edge", "prelu"),
+    (64, 24, 256, 12, 1, "mr", "relu"),
+    (32, 40, 384, 20, 1, "mr", "relu"),
+])
+def test_wide_consumer_matches_generic_and_oracle(cfg):
+    """Channel counts 32 / 64 / 128 take the float4 half-warp-per-query consumer of the tensor-core
+    kernel (cta_epilogue_wide): same numbers as the generic consumer of the fp32 kernel and as the
+    oracle, with negative BatchNorm scales (min branch), a negative PReLU slope (non-monotone
+    activation) and train-mode batch statistics."""
+    from deep_gcns_torch_b200 import _native
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    C, co, N, k, d, conv, act = cfg
+    g = torch.Generator().manual_seed(C * 1000 + co)
+    torch.manual_seed(3)
+    mod = D.DynConv2d(C, co, k, d, conv, act, "batch", True)
+    for m in mod.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data = torch.randn(co, generator=g)              # about half negative
+            m.bias.data = torch.randn(co, generator=g) * 0.2
+            m.running_mean.data = torch.randn(co, generator=g) * 0.3
+            m.running_var.data = torch.rand(co, generator=g) + 0.4
+        if isinstance(m, torch.nn.PReLU):
+            m.weight.data.fill_(-0.3)
+    x = torch.randn(2, C, N, 1, generator=g)
+    p = od.params_from_module(mod.gconv.nn)
+    ref_ei = od.knn_matrix(x, k * d)[:, :, :, ::d]
+    ref_y = od.graph_conv(x, ref_ei, p, conv, act, "batch")
+    mod = mod.cuda()
+    xc = x.cuda()
+    try:
+        for train in (False, True):
+            mod.train(train)
+            _native.set_knn_path("ffma")
+            with torch.no_grad():
+                y_ref = mod(xc)
+            _native.set_knn_path("tc")
+            with torch.no_grad():
+                y = mod(xc)
+            torch.testing.assert_close(y, y_ref, rtol=2e-5, atol=2e-6)
+            if not train:
+                ei = mod.dilated_knn_graph(xc)
+                same = (ei[0].cpu().sort(-1).values == ref_ei[0].sort(-1).values).all(-1)
+                assert same.float().mean() > 0.99
+                mask = same.unsqueeze(1).unsqueeze(-1).expand_as(ref_y)
+                torch.testing.assert_close(y.cpu()[mask], ref_y[mask], rtol=RTOL, atol=ATOL)
+    finally:
+        _native.set_knn_path("auto")
+
+
 def test_tensor_core_prefilter_clustered_cloud_falls_back_exactly():
     """Many near-identical points defeat the certification margin: those queries must be
     completed by the exact kernel and still match the fp32 path bit for bit."""
