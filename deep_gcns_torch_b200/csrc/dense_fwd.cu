@@ -171,12 +171,18 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
   const double pq = static_cast<double>(K) / N;
   int sample_rank = static_cast<int>(128.0 * pq + 2.5 * sqrt(128.0 * pq * (1.0 - pq)) + 2.0) + 1;
   if (sample_rank > 127) sample_rank = 127;
-  const int64_t expect = static_cast<int64_t>(1.35 * (sample_rank + 1) / 128.0 * N) + 32;
-  int cap = next_pow2(static_cast<int>(expect > 2 * K ? expect : 2 * K));
+  // room for every key below the bound (no power of two needed: only the wanted bins get sorted);
+  // k > 64 keeps the full sort and needs the padded power of two
+  // keys below a bound at sample rank r: mean (r+1)/129 N, relative spread ~ 1/sqrt(r+1); leave 3.5 sigma
+  const double wmean = (sample_rank + 1) / 129.0 * N;
+  const int64_t wcap = static_cast<int64_t>(wmean * (1.0 + 3.5 / sqrt(sample_rank + 1.0))) + 32;
+  int cap = static_cast<int>(wcap > K + 64 ? wcap : K + 64);
+  cap = a.k > 64 ? next_pow2(cap > 2 * K ? cap : 2 * K) : (cap + 31) / 32 * 32;
+  if (cap < 128) cap = 128;            // the sorted sample lives in the same array
   if (cap > 2048) cap = 2048;
   const bool fast = N >= 512 && cap >= K;
   const size_t per_warp_f = static_cast<size_t>(cap) * 8 + static_cast<size_t>((a.k + 31) / 32 * 32) * 4 + 2560;   // keys, sel, multi-select tables (hist 256, prefix 260 ints, 256 marks -> 2320 B)
-  int warps_f = static_cast<int>((100u << 10) / per_warp_f);
+  int warps_f = static_cast<int>((56u << 10) / per_warp_f);   // <= 56 KB per CTA: four CTAs per SM
   if (warps_f > 8) warps_f = 8;
   if (warps_f < 1) warps_f = 1;
   const size_t smem_f = per_warp_f * warps_f;

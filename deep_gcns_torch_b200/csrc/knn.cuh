@@ -841,14 +841,25 @@ __global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const f
     if ((rank >> 5) == 2) bound = __shfl_sync(0xffffffffu, smp[2], rank & 31);
     if ((rank >> 5) == 3) bound = __shfl_sync(0xffffffffu, smp[3], rank & 31);
     w = 0;
+    float nxt[4];                        // the next 128 distances are in flight while these are compacted
+#pragma unroll
+    for (int u = 0; u < 4; ++u) nxt[u] = (u * 32 + lane < N) ? __ldg(drow + u * 32 + lane) : 0.f;
     for (int i0 = 0; i0 < N; i0 += 128) {
       uint32_t key[4];
       bool take[4];
+      float cur[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + 128 + u * 32 + lane;
+        if (i < N) nxt[u] = __ldg(drow + i);
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + u * 32 + lane;
         key[u] = 0xFFFFFFFFu;
-        if (i < N) key[u] = float_to_ordered(__ldg(drow + i));
+        if (i < N) key[u] = float_to_ordered(cur[u]);
         take[u] = (i < N) && key[u] <= bound && !(a.exclude_self && i == q);
       }
 #pragma unroll
@@ -880,6 +891,10 @@ __global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const f
   if (k > 64) {   // many kept ranks: plain sort of everything below the bound
     int KP = 128;
     while (KP < w) KP <<= 1;
+    if (KP > CAP) {
+      if (lane == 0) row_list[atomicAdd(row_count, 1)] = static_cast<int>(row);
+      return;
+    }
     for (int i = w + lane; i < KP; i += 32) sk[i] = KEY_MAX;
     __syncwarp();
     warp_bitonic_sort(sk, KP, lane);
@@ -979,6 +994,10 @@ __global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const f
   }
   int TP = 32;
   while (TP < T) TP <<= 1;
+  if (TP > CAP) {   // (massive ties inside the wanted bins) no room to pad the sort: exact kernel
+    if (lane == 0) row_list[atomicAdd(row_count, 1)] = static_cast<int>(row);
+    return;
+  }
   __syncwarp();
   for (int i = T + lane; i < TP; i += 32) sk[i] = KEY_MAX;
   __syncwarp();
