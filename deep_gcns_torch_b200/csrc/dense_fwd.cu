@@ -43,6 +43,7 @@ size_t knn_workspace_bytes(int64_t B, int64_t C, int64_t N, int64_t K) {
     bytes += align_up(static_cast<size_t>(B) * TC_PLANES * cpad * N * 2, 256);   // bf16 planes
     bytes += align_up(static_cast<size_t>(B) * N * C * 4, 256);          // node-major copy
     bytes += align_up(static_cast<size_t>(B) * 4, 256);                  // per-cloud max |x|^2
+    bytes += align_up(static_cast<size_t>(B) * 8 * N * 2, 256);          // -|x|^2/2 operand block
     bytes += align_up(static_cast<size_t>(B) * N * 4 + 256, 256);        // fail counter + list
   }
   if (K > SMALL_K_MAX) {
@@ -66,18 +67,20 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
   __nv_bfloat16* planes = ws.take<__nv_bfloat16>(static_cast<size_t>(B) * TC_PLANES * cpad * N);
   float* xt_own = xt ? nullptr : ws.take<float>(static_cast<size_t>(B) * N * C);
   float* sqmax = ws.take<float>(static_cast<size_t>(B));
+  __nv_bfloat16* sqp = ws.take<__nv_bfloat16>(static_cast<size_t>(B) * 8 * N);
   int* fail = ws.take<int>(static_cast<size_t>(B) * N + 64);
   if (!ws.ok) return DGCN_ERR_WORKSPACE;
   DGCN_CUDA_TRY(cudaMemsetAsync(fail, 0, 256, stream));
   DGCN_CUDA_TRY(cudaMemsetAsync(sqmax, 0, static_cast<size_t>(B) * 4, stream));
   // sq, bf16 planes, node-major copy and max |x|^2 in one pass over x (sq overwrites what the caller computed)
   tc_prologue_kernel<<<dim3(ceil_div(N, 32), B), 256, 0, stream>>>(a.x, a.sb, a.sc, C, cpad, N, const_cast<float*>(a.sq),
-                                                               planes, xt ? nullptr : xt_own, sqmax);
+                                                               planes, xt ? nullptr : xt_own, sqmax, sqp);
   DGCN_LAUNCH_CHECK();
   if (!xt) xt = xt_own;
   TcArgs t{};
   t.a = a;
   t.planes = planes;
+  t.sqp = sqp;
   t.xt = xt;
   t.xt32 = (reinterpret_cast<uintptr_t>(xt) & 31) == 0 ? 1 : 0;
   t.sqmax = sqmax;

@@ -72,6 +72,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spin > (1u << 26)) __trap();
   }
 }
+__device__ __forceinline__ void cp_async16_addr(uint32_t smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -163,12 +166,12 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t sb, int64
 }
 
 // One pass over x for everything the tensor-core path needs: sq (B,N) (same FMA chain as sqnorm_kernel),
-// the bf16 planes, the node-major copy xt (optional) and the per-cloud max of sq (atomicMax on the bits of
+// the bf16 planes, the extra operand block sqp that folds -|x_j|^2/2 into the tensor-core product, the node-major copy xt (optional) and the per-cloud max of sq (atomicMax on the bits of
 // a non-negative float; sqmax must be zero-initialised).  Block = 32 points x all channels (C <= 64).
 __global__ void __launch_bounds__(256) tc_prologue_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C,
                                                          int Cpad, int N, float* __restrict__ sq,
                                                          __nv_bfloat16* __restrict__ planes, float* __restrict__ xt,
-                                                         float* __restrict__ sqmax) {
+                                                         float* __restrict__ sqmax, __nv_bfloat16* __restrict__ sqp) {
   __shared__ float tile[TC_MAX_C][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int b = blockIdx.y, n0 = blockIdx.x * 32, n = n0 + tx;
@@ -188,7 +191,20 @@ __global__ void __launch_bounds__(256) tc_prologue_kernel(const float* __restric
   if (ty == 0) {
     float s = 0.f;
     for (int c = 0; c < C; ++c) s = fmaf(tile[c][tx], tile[c][tx], s);
-    if (n < N) sq[static_cast<int64_t>(b) * N + n] = s;
+    if (n < N) {
+      sq[static_cast<int64_t>(b) * N + n] = s;
+      // rows 0..2 of the (B, 8, N) extra operand block: -|x|^2 / 2 as three bf16 terms (2^-24 relative)
+      __nv_bfloat16* sp = sqp + static_cast<int64_t>(b) * 8 * N + n;
+      float rem = -0.5f * s;
+#pragma unroll
+      for (int t3 = 0; t3 < 3; ++t3) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+        sp[static_cast<int64_t>(t3) * N] = h;
+        rem -= __bfloat162float(h);
+      }
+#pragma unroll
+      for (int t3 = 3; t3 < 8; ++t3) sp[static_cast<int64_t>(t3) * N] = __float2bfloat16_rn(0.f);
+    }
     float m = n < N ? s : 0.f;
     m = warp_max(m);
     if (tx == 0) atomicMax(reinterpret_cast<unsigned int*>(sqmax + b), __float_as_uint(m));
@@ -227,7 +243,8 @@ __device__ __forceinline__ void ldg256(const float* p, float (&w)[8]) {
 
 struct TcArgs {
   KnnArgs a;
-  const __nv_bfloat16* planes;   // (B,3,Cpad,N)
+  const __nv_bfloat16* planes;   // (B,2,Cpad,N)
+  const __nv_bfloat16* sqp;      // (B,8,N): rows 0..2 = bf16 split of -|x|^2/2, rest zero
   const float* xt;               // (B,N,C) node-major fp32 copy (exact re-rank)
   const float* sqmax;            // (B)
   int Cpad;
@@ -245,16 +262,18 @@ constexpr int TC_BUF = 16;                            // 8-byte slots per thread
 constexpr int TC_FLUSH_EARLY = 10;                    // packed 4-byte entries: 32 slots; tight threshold while the
 constexpr int TC_FLUSH_LATE = 10;                     // list still moves a lot (first tiles), fuller batches afterwards
 constexpr int TC_STAGE_BYTES = TC_PLANES * 2 * TC_MAX_C * 128;   // 32 KB: planes x 2 MN blocks x 64 rows x 128 B
+constexpr int TC_XBLOCK_BYTES = 2 * 16 * 128;                    // 4 KB: one extra K=16 block, 2 MN blocks x 16 rows x 128 B
 
 // Shared memory of one CTA (128 queries of one cloud).  Several CTAs share an SM so that the
 // latency-bound phases of one (exact re-rank, neighbour gather) overlap the streaming phase of another.
-//   work (1024-aligned, work_bytes): while streaming [query planes 32 KB | candidate stage 32 KB], both
-//   canonical MN-major SWIZZLE_128B: [plane][mn_block(2)][Cpad rows][128 B]; afterwards
+//   work (1024-aligned, work_bytes): while streaming [query planes 32 KB | candidate stage 32 KB |
+//   query extra block 4 KB | candidate extra block 4 KB], all canonical MN-major SWIZZLE_128B:
+//   [plane][mn_block(2)][Cpad rows][128 B]; the extra K=16 blocks hold ones (query side, rows 0..2) and the
+//   bf16 split of -|x_j|^2/2 (candidate side), so the accumulator is x_i.x_j - |x_j|^2/2; afterwards
 //   [exact-sorted lists KP x 128 x 8 B | sel 128 x sel_ld x 4 B | consumer scratch].
 //   tail: the fixed-size part below.
 struct TcTail {
   uint64_t cbuf[TC_BUF * TC_THREADS];               // 16 KB private candidate buffers, slot-major
-  float sqj[3][TILE];                               // [tile % 3][column]
   uint64_t mbar;                                    // MMA of a tile has completed (tcgen05.commit)
   uint64_t mbar_ready;                              // all 128 threads: next tile's operands landed, other accumulator drained
   uint32_t tmem_base;
@@ -269,7 +288,7 @@ __host__ __device__ inline size_t tc_work_bytes(int KP, int k, bool wide, int nc
   after = (after + 15) & ~static_cast<size_t>(15);
   if (wide) after += static_cast<size_t>(TC_THREADS / 32) * 2 * nch * 4;             // red
   else after += 2 * static_cast<size_t>(32) * STAGE_LD * 4 + 2 * (TC_THREADS / 32) * 32 * 4 + 256;   // stage_max, stage_min, red
-  const size_t stream = 2 * static_cast<size_t>(TC_STAGE_BYTES);
+  const size_t stream = 2 * static_cast<size_t>(TC_STAGE_BYTES) + 2 * TC_XBLOCK_BYTES;
   const size_t w = after > stream ? after : stream;
   return (w + 1023) & ~static_cast<size_t>(1023);
 }
@@ -344,9 +363,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, 256);     // two 128-column accumulators
   const int ntiles = N / TILE;
+  unsigned char* qx = work + 2 * TC_STAGE_BYTES;          // query-side extra block: ones in K rows 0..2
+  unsigned char* sx = qx + TC_XBLOCK_BYTES;               // candidate-side extra block: -|x_j|^2/2 split in rows 0..2
+  const __nv_bfloat16* sqp_b = t.sqp + static_cast<int64_t>(b) * 8 * N;
+  for (int ch = tid; ch < TC_XBLOCK_BYTES / 16; ch += TC_THREADS) {   // whole rows are constant: no swizzle needed
+    const int row = (ch >> 3) & 15;
+    const uint32_t one2 = row < 3 ? 0x3F803F80u : 0u;
+    reinterpret_cast<uint4*>(qx)[ch] = make_uint4(one2, one2, one2, one2);
+    reinterpret_cast<uint4*>(sx)[ch] = make_uint4(0u, 0u, 0u, 0u);        // rows 8..15 stay zero
+  }
+  __syncthreads();                                        // the zero fill precedes the cp.async writes of rows 0..7
+  // candidate extra block: thread r moves 16-byte chunk (r & 15) of K row (r >> 4) (rows 0..7)
+  const uint32_t sx_dst = smem_u32(sx) + ((r & 15) >> 3) * 2048 + (r >> 4) * 128 + ((((r & 15) & 7) ^ (r >> 4)) << 4);
+  const __nv_bfloat16* sx_src = sqp_b + static_cast<int64_t>(r >> 4) * N + (r & 15) * 8;
   tc_load_tile(qstage, planes_b, Cpad, N, q0, r);
   tc_load_tile(stage, planes_b, Cpad, N, 0, r);
-  sm.sqj[0][r] = __ldg(sqb + r);
+  cp_async16_addr(sx_dst, sx_src);
   cp_async_commit();
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
   // One thread issues the 4 x Cpad/16 MMAs of a candidate tile into accumulator `buf` and commits.
@@ -365,6 +397,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
         acc = 1;
       }
     }
+    // + 1 x (-|x_j|^2/2): the accumulator becomes x_i.x_j - |x_j|^2/2 = -key/2
+    umma_bf16(tmem_acc, umma_desc_mn_sw128(smem_u32(qx), 2048, 1024), umma_desc_mn_sw128(smem_u32(sx), 2048, 1024),
+              kIdescBf16MnMn128x128, 1u);
     umma_commit(&sm.mbar);
   };
   cp_async_wait_all();
@@ -385,6 +420,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
   }
   const float sqq = __ldg(sqb + qg);
   float tau_f = __uint_as_float(0x7FC00000u);     // NaN admits everything until the list is full
+  float thr_acc = tau_f;
   // private candidate buffer, slot-major: PACKED 32 slots x 4 B (key bits | 12-bit index), else 16 x 8 B
   constexpr uint32_t ESZ = PACKED ? 4u : 8u;
   const uint32_t cb_addr0 = smem_u32(sm.cbuf) + tid * ESZ;
@@ -418,13 +454,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
       }
       if (e < cnt) {
         if (PACKED) {
-          // entry = key bits with the low 12 mantissa bits replaced by the index; restore a LOWER bound of the key
-          const uint32_t kb = (en & 0x80000000u) ? (en | 0xFFFu) : (en & 0xFFFFF000u);
-          const float d2 = fmaxf(__uint_as_float(kb) + sqq, 0.f);
+          // entry = accumulator bits (acc = -key/2) with the low 12 mantissa bits replaced by the index;
+          // restore an UPPER bound of acc, i.e. a lower bound of the key
+          const uint32_t ab = (en & 0x80000000u) ? (en & 0xFFFFF000u) : (en | 0xFFFu);
+          const float d2 = fmaxf(fmaf(-2.0f, __uint_as_float(ab), sqq), 0.f);
           nk = (__float_as_uint(d2) & 0xFFFFF000u) | (en & 0xFFFu);
         } else {
-          nv = static_cast<uint32_t>(kv);              // low word = index, high word = float key bits
-          nk = float_to_ordered(__uint_as_float(static_cast<uint32_t>(kv >> 32)));
+          nv = static_cast<uint32_t>(kv);              // low word = index, high word = accumulator bits
+          nk = float_to_ordered(-2.0f * __uint_as_float(static_cast<uint32_t>(kv >> 32)));
         }
       }
       if (nk < lk[KP - 1]) {
@@ -439,26 +476,26 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
     } else {
       tau_f = ordered_to_float(lk[KP - 1]);        // NaN while the list is not full
     }
+    thr_acc = -0.5f * tau_f;                        // the filter compares accumulators: key <= tau  <=>  acc >= -tau/2
   };
 
   // Pipeline per tile t: wait MMA(t) -> the stage is free: cp.async tile t+1 -> filter first half of
-  // accumulator t&1 -> (loads landed) barrier, issue MMA(t+1) into the other accumulator -> filter
-  // second half.  The only CTA barrier per tile also orders: every thread finished reading accumulator
-  // (t+1)&1 (tile t-1) and sqj[(t+2)%3] (tile t-1) before they are overwritten.
+  // accumulator t&1 -> (loads landed) split barrier, issue MMA(t+1) into the other accumulator -> filter
+  // second half.  The split barrier also orders: every thread finished reading accumulator (t+1)&1
+  // (tile t-1) before it is overwritten.
   for (int tile = 0; tile < ntiles; ++tile) {
     const int par = tile & 1;
     const bool more = tile + 1 < ntiles;
-    const float sq_next = more ? __ldg(sqb + (tile + 1) * TILE + r) : 0.f;
     mbar_wait(&sm.mbar, static_cast<uint32_t>(par));
     tc_fence_after();
     if (more) {
       tc_load_tile(stage, planes_b, Cpad, N, (tile + 1) * TILE, r);
+      cp_async16_addr(sx_dst, sx_src + (tile + 1) * TILE);
       cp_async_commit();
-      sm.sqj[(tile + 1) % 3][r] = sq_next;
     }
-    // filter: thread = TMEM lane = query; approx key = |x_j|^2 - 2 x_i.x_j (row-constant |x_i|^2 omitted)
+    // filter: thread = TMEM lane = query; the accumulator is -key/2 with key = |x_j|^2 - 2 x_i.x_j
+    // (row-constant |x_i|^2 omitted): admit when acc >= -tau/2
     const int j0 = tile * TILE;
-    const float4* sqj4 = reinterpret_cast<const float4*>(sm.sqj[tile % 3]);
     const bool diag = a.exclude_self && j0 == q0;
     const uint32_t tacc = tmem + static_cast<uint32_t>(par * TILE) + lane_base;
     const uint32_t flush_bytes = PACKED ? (tile < 2 ? t.flush_early : t.flush_late) * TC_THREADS * 4u
@@ -483,27 +520,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
       if (diag && (r >> 5) == cchunk) {   // self exclusion: only in the diagonal tile, only one column
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (i == (r & 31)) v[i] = -INFINITY;   // key becomes +inf
+          if (i == (r & 31)) v[i] = -INFINITY;   // accumulator -inf = key +inf
       }
       // PACKED: one LOP3 builds the entry (key & R & I) | (R ^ I) with R = ~0xFFF | index bits 5..11
       // (tile, chunk) and the immediate I = ~0xFFF | index bits 0..4
       const uint32_t rbits = 0xFFFFF000u | static_cast<uint32_t>(j0 + cchunk * 32);
-      // |x_j|^2 of the next 8 columns is fetched before this group's buffer stores (shared-memory
-      // loads cannot be hoisted over stores by the assembler)
-      float4 n0 = sqj4[cchunk * 8], n1 = sqj4[cchunk * 8 + 1];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const float4 s0 = n0, s1 = n1;
-        if (g < 3) {
-          n0 = sqj4[cchunk * 8 + g * 2 + 2];
-          n1 = sqj4[cchunk * 8 + g * 2 + 3];
-        }
-        const float sq8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         uint32_t jcur = static_cast<uint32_t>(j0 + cchunk * 32 + g * 8);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float key = fmaf(-2.0f, v[g * 8 + i], sq8[i]);
-          // if (!(key > tau)) { buffer[slot] = entry; ++slot; }  - predicated, no branch
+          const float acc = v[g * 8 + i];
+          // if (!(acc < thr_acc)) { buffer[slot] = entry; ++slot; }  - predicated, no branch
           if (PACKED) {
             const uint32_t ibits = 0xFFFFF000u | static_cast<uint32_t>(g * 8 + i);
             asm volatile(
@@ -511,22 +539,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
                 ".reg .pred p;\n"
                 ".reg .b32 en;\n"
                 "lop3.b32 en, %1, %2, %5, 0xE6;\n"          // (a & b & c) | (b ^ c)
-                "setp.leu.f32 p, %1, %3;\n"
+                "setp.geu.f32 p, %1, %3;\n"
                 "@p st.shared.b32 [%0], en;\n"
                 "@p add.u32 %0, %0, %4;\n"
                 "}"
                 : "+r"(cb_addr)
-                : "r"(__float_as_uint(key)), "r"(rbits), "f"(tau_f), "n"(TC_THREADS * 4), "r"(ibits));
+                : "r"(__float_as_uint(acc)), "r"(rbits), "f"(thr_acc), "n"(TC_THREADS * 4), "r"(ibits));
           } else {
             asm volatile(
                 "{\n"
                 ".reg .pred p;\n"
-                "setp.leu.f32 p, %1, %3;\n"
+                "setp.geu.f32 p, %1, %3;\n"
                 "@p st.shared.v2.b32 [%0], {%2, %1};\n"
                 "@p add.u32 %0, %0, %4;\n"
                 "}"
                 : "+r"(cb_addr)
-                : "f"(key), "r"(jcur), "f"(tau_f), "n"(TC_THREADS * 8));
+                : "f"(acc), "r"(jcur), "f"(thr_acc), "n"(TC_THREADS * 8));
             ++jcur;
           }
         }
@@ -618,9 +646,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
       const float dk = ordered_to_float(static_cast<uint32_t>(kth >> 32));
       const float smax = __ldg(t.sqmax + b);
       // |approx - exact fp32| <= eps: 4 bf16 products of the (hi, mid) split (2^-15.5 rel. to |x_i||x_j|),
-      // ~4*Cpad fp32 tensor-core accumulations and Cpad FMA-chain roundings (2^-23 each), the final additions.
+      // ~4*Cpad fp32 tensor-core accumulations and Cpad FMA-chain roundings (2^-23 each), the -|x_j|^2/2 term
+      // accumulated with them (3-term bf16 split, roundings at magnitude <= smax/2) and the final additions (2^-20).
       const float eps = (2.0f * (2.158e-5f + (5.0f * Cpad + 8.0f) * 1.1921e-7f)) * sqrtf(sqq * smax) +
-                        4.768e-7f * (sqq + smax);
+                        9.537e-7f * (sqq + smax);
       ok = (dk + eps < (PACKED ? cut : cut + sqq));
     }
     sm.ok[r] = ok ? 1 : 0;
