@@ -56,15 +56,64 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.
+
+    The timed region of the default run lasts ~10 ms, far below nvidia-smi's 100-200 ms loop period, so the
+    samples come from NVML directly (the library nvidia-smi itself reads: `clocks.sm`, `clocks.max.sm`,
+    `clocks_event_reasons.*`), polled from a thread every ~0.5 ms between __enter__ and __exit__; the
+    nvidia-smi loop of the profiling recipe is the fallback when pynvml is unavailable."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReasons bits
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.samples, self.max_mhz, self.reasons = [], 0.0, set()
+        self.nvml, self.handle, self.stop = None, None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+                handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml, self.handle = pynvml, handle
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll_once(self):
+        nv = self.nvml
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        for name, bit in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _poll(self):
+        while not self.stop.is_set():
+            try:
+                self._poll_once()
+            except Exception:
+                return
+            time.sleep(0.0005)
 
     def __enter__(self):
+        self.stop.clear()
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
@@ -81,6 +130,14 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def __exit__(self, *exc):
+        if self.nvml is not None:
+            try:
+                self._poll_once()            # the GPU is still inside (or just leaving) the timed region
+            except Exception:
+                pass
+            self.stop.set()
+            self.thread.join(timeout=2)
+            return
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -89,7 +146,7 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, reasons = list(self.samples), self.max_mhz, set(self.reasons)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for row in self.rows:
             parts = [p.strip() for p in row.split(",")]
@@ -105,7 +162,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi -lms 100"}
 
 
 def oracle_layer(threads):
@@ -236,13 +293,14 @@ def run_native(args):
         e2e_loop(4)
         barrier()
         b2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b2.record(cur)
-        h2d.wait_event(b2)
-        e2e_loop(args.steps)
-        cur.wait_stream(d2h)
-        cur.wait_stream(h2d)
-        e2.record(cur)
-        barrier()
+        with clocks:                                     # the end-to-end region is sampled as well
+            b2.record(cur)
+            h2d.wait_event(b2)
+            e2e_loop(args.steps)
+            cur.wait_stream(d2h)
+            cur.wait_stream(h2d)
+            e2.record(cur)
+            barrier()
         ms_e2e = b2.elapsed_time(e2)
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
