@@ -334,7 +334,7 @@ def run_native(args):
                 "h2d_bytes_per_step": B * C * N * 4, "d2h_bytes_per_step": B * C * N * 4,
                 "ms_per_step": ms_e2e / args.steps},
         # pack_edge_weights, node_pq, tc_prologue, knn_tc, knn_exact_rows per step
-        "gpu_launches": 5 * args.steps,
+        "gpu_launches": 4 * args.steps,   # pack weights, fused prologue + node GEMM, tensor-core selection + consumer, exact completion
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "knn_tc_kernel<24,packed> (tcgen05 bf16 (hi,mid) pre-filter + exact fp32 "
                                                  "re-rank + certificate + fused EdgeConv gather/max)",

@@ -61,7 +61,8 @@ static int next_pow2(int v) {
 }
 
 // Tensor-core pre-filter path (knn_tc.cuh).  xt: node-major copy of x if the caller has one.
-static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const float* xt, int64_t* n_partial) {
+static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const float* xt, int64_t* n_partial,
+                         const ProloguePq* pqf) {
   const int B = a.B, N = a.N, C = a.C, K = a.K;
   const int cpad = (C + 15) / 16 * 16;
   __nv_bfloat16* planes = ws.take<__nv_bfloat16>(static_cast<size_t>(B) * TC_PLANES * cpad * N);
@@ -73,8 +74,17 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
   DGCN_CUDA_TRY(cudaMemsetAsync(fail, 0, 256, stream));
   DGCN_CUDA_TRY(cudaMemsetAsync(sqmax, 0, static_cast<size_t>(B) * 4, stream));
   // sq, bf16 planes, node-major copy and max |x|^2 in one pass over x (sq overwrites what the caller computed)
-  tc_prologue_kernel<<<dim3(ceil_div(N, 32), B), 256, 0, stream>>>(a.x, a.sb, a.sc, C, cpad, N, const_cast<float*>(a.sq),
-                                                               planes, xt ? nullptr : xt_own, sqmax, sqp);
+  if (pqf) {   // the EdgeConv node GEMM rides on the same pass over x
+    const size_t smem = (static_cast<size_t>(TC_MAX_C) * 68 + static_cast<size_t>(C) * pqf->M) * 4;
+    DGCN_CUDA_TRY(cudaFuncSetAttribute(tc_prologue_pq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    tc_prologue_pq_kernel<<<dim3(N / 64, B), 256, smem, stream>>>(a.x, a.sb, a.sc, C, cpad, N, const_cast<float*>(a.sq),
+                                                                  planes, xt ? nullptr : xt_own, sqmax, sqp, *pqf);
+  } else {
+    tc_prologue_kernel<<<dim3(ceil_div(N, 32), B), 256, 0, stream>>>(a.x, a.sb, a.sc, C, cpad, N,
+                                                                 const_cast<float*>(a.sq), planes,
+                                                                 xt ? nullptr : xt_own, sqmax, sqp);
+  }
   DGCN_LAUNCH_CHECK();
   if (!xt) xt = xt_own;
   TcArgs t{};
@@ -134,14 +144,27 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
 
 // Runs the selection (+ fused consumer described by a.epi) on `stream`.
 // n_partial (optional out): number of train-mode statistic rows the chosen path wrote.
-int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partial = nullptr) {
+// true when launch_knn will take the tensor-core path for these arguments
+static bool knn_takes_tc(const KnnArgs& a) {
+  const bool train_wide = a.epi.mode == EPI_EDGE && a.epi.norm == DGCN_NORM_BATCH_TRAIN && a.epi.c_out > 128;
+  return tc_enabled() && tc_shape_ok(a.C, a.N, a.K) && a.k <= SEL_LD && !train_wide;
+}
+// the fused prologue can also produce PQ (EdgeConv): channel / output counts it supports
+static bool prologue_pq_ok(const KnnArgs& a, int64_t M) {
+  return knn_takes_tc(a) && M % 128 == 0 && M <= 256 && a.C <= TC_MAX_C;
+}
+
+// pqf (optional): produce the EdgeConv node GEMM inside the tensor-core prologue; the caller must have
+// checked prologue_pq_ok and skipped node_pq_kernel.
+int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partial = nullptr,
+               const ProloguePq* pqf = nullptr) {
   const int B = a.B, N = a.N, K = a.K;
   float* sq = ws.take<float>(static_cast<size_t>(B) * N);
   if (!ws.ok) return DGCN_ERR_WORKSPACE;
   a.sq = sq;
-  const bool train_wide = a.epi.mode == EPI_EDGE && a.epi.norm == DGCN_NORM_BATCH_TRAIN && a.epi.c_out > 128;
-  if (tc_enabled() && tc_shape_ok(a.C, N, K) && a.k <= SEL_LD && !train_wide)
-    return launch_knn_tc(a, ws, stream, a.epi.mode == EPI_MR ? a.epi.xt : nullptr, n_partial);
+  if (knn_takes_tc(a))
+    return launch_knn_tc(a, ws, stream, a.epi.mode == EPI_MR ? a.epi.xt : nullptr, n_partial, pqf);
+  if (pqf) return DGCN_ERR_BAD_ARG;   // (internal misuse) nobody would produce PQ
   sqnorm_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(a.x, a.sb, a.sc, a.C, N, sq);
   DGCN_LAUNCH_CHECK();
   const dim3 grid(ceil_div(N, TILE), B);
@@ -588,20 +611,27 @@ static int conv_forward(int conv, const float* x, int64_t B, int64_t ci, int64_t
     pack_edge_weights_kernel<<<static_cast<unsigned>(ceil_div(ci * M > M ? ci * M : M, 256)), 256, 0, stream>>>(
         p->weight, p->bias, static_cast<int>(ci), static_cast<int>(co), wk, bk);
     DGCN_LAUNCH_CHECK();
-    node_pq_kernel<<<dim3(ceil_div(M, TILE), ceil_div(N, TILE), B), NTHREADS, 0, stream>>>(
-        x, sb, sc, static_cast<int>(ci), static_cast<int>(N), vec, wk, bk, M, pq);
-    DGCN_LAUNCH_CHECK();
     e.mode = EPI_EDGE;
     e.pq = pq;
     e.out = out;
     e.out_min = out_min;
     e.partial = partial;
+    KnnArgs a;
+    bool pq_in_prologue = false;
     if (fused) {
-      KnnArgs a;
       int rc = fill_knn_args(a, x, B, ci, N, sb, sc, dil, 0);
       if (rc != DGCN_OK) return rc;
       a.epi = e;
-      rc = launch_knn(a, ws, stream, &pl.n_partial);
+      pq_in_prologue = prologue_pq_ok(a, M);   // the tensor-core prologue computes PQ on its pass over x
+    }
+    if (!pq_in_prologue) {
+      node_pq_kernel<<<dim3(ceil_div(M, TILE), ceil_div(N, TILE), B), NTHREADS, 0, stream>>>(
+          x, sb, sc, static_cast<int>(ci), static_cast<int>(N), vec, wk, bk, M, pq);
+      DGCN_LAUNCH_CHECK();
+    }
+    if (fused) {
+      const ProloguePq pqf{wk, bk, pq, static_cast<int>(M)};
+      int rc = launch_knn(a, ws, stream, &pl.n_partial, pq_in_prologue ? &pqf : nullptr);
       if (rc != DGCN_OK) return rc;
     } else {
       GatherArgs g{e, edge_index, nbr, static_cast<int>(B), static_cast<int>(N), static_cast<int>(k)};

@@ -217,6 +217,101 @@ __global__ void __launch_bounds__(256) tc_prologue_kernel(const float* __restric
   }
 }
 
+// tc_prologue_kernel fused with the EdgeConv node GEMM PQ[b][n][m] = sum_c x[b][c][n] wk[c][m] + bk[m]
+// (node_pq_kernel's result bit for bit: fp32 FMA chain over c ascending from 0, bias added last), so x is
+// read once for everything the layer needs.  Block = 64 points x all channels (C <= 64); M % 128 == 0,
+// N % 64 == 0.  Dynamic shared memory: xs[C][68] + ws[C][M] floats.
+struct ProloguePq {
+  const float* wk;   // [C][M] packed weights (pack_edge_weights_kernel)
+  const float* bk;   // [M]
+  float* pq;         // (B, N, M)
+  int M;
+};
+__global__ void __launch_bounds__(256) tc_prologue_pq_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C,
+                                                            int Cpad, int N, float* __restrict__ sq,
+                                                            __nv_bfloat16* __restrict__ planes, float* __restrict__ xt,
+                                                            float* __restrict__ sqmax, __nv_bfloat16* __restrict__ sqp,
+                                                            const ProloguePq g) {
+  extern __shared__ __align__(16) float pq_smem[];
+  constexpr int XLD = 68;
+  float* xs = pq_smem;                       // [C][XLD]
+  float* ws = pq_smem + TC_MAX_C * XLD;      // [C][M]
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y, n0 = blockIdx.x * 64;
+  const int M = g.M;
+  const int64_t plane = static_cast<int64_t>(Cpad) * N;
+  __nv_bfloat16* pb = planes + static_cast<int64_t>(b) * TC_PLANES * plane;
+  {
+    const int tx = tid & 63, ty = tid >> 6, n = n0 + tx;
+    for (int c = ty; c < Cpad; c += 4) {
+      const float v = c < C ? __ldg(x + b * sb + c * sc + n) : 0.f;
+      if (c < C) xs[c * XLD + tx] = v;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      pb[static_cast<int64_t>(c) * N + n] = hi;
+      pb[plane + static_cast<int64_t>(c) * N + n] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+  }
+  for (int i = tid * 4; i < C * M; i += 256 * 4)
+    *reinterpret_cast<float4*>(ws + i) = __ldg(reinterpret_cast<const float4*>(g.wk + i));
+  __syncthreads();
+  if (tid < 64) {
+    const int n = n0 + tid;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(xs[c * XLD + tid], xs[c * XLD + tid], s);
+    sq[static_cast<int64_t>(b) * N + n] = s;
+    __nv_bfloat16* sp = sqp + static_cast<int64_t>(b) * 8 * N + n;
+    float rem = -0.5f * s;
+#pragma unroll
+    for (int t3 = 0; t3 < 3; ++t3) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+      sp[static_cast<int64_t>(t3) * N] = h;
+      rem -= __bfloat162float(h);
+    }
+#pragma unroll
+    for (int t3 = 3; t3 < 8; ++t3) sp[static_cast<int64_t>(t3) * N] = __float2bfloat16_rn(0.f);
+    const float m = warp_max(s);
+    if ((tid & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(sqmax + b), __float_as_uint(m));
+  }
+  if (xt) {
+    for (int i = tid; i < 64 * C; i += 256) {
+      const int rr = i / C, c = i - rr * C;
+      xt[(static_cast<int64_t>(b) * N + n0 + rr) * C + c] = xs[c * XLD + rr];
+    }
+  }
+  // node GEMM: thread (tx, ty) owns points 4 ty .. 4 ty + 3 and outputs {4 tx .. +3} U {64 + 4 tx .. +3} of each
+  // 128-wide pass
+  const int tx = tid & 15, ty = tid >> 4;
+  for (int m0 = 0; m0 < M; m0 += 128) {
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) {
+      const float4 a = *reinterpret_cast<const float4*>(xs + c * XLD + ty * 4);
+      const float4 w0 = *reinterpret_cast<const float4*>(ws + c * M + m0 + tx * 4);
+      const float4 w1 = *reinterpret_cast<const float4*>(ws + c * M + m0 + 64 + tx * 4);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bk + m0 + tx * 4));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bk + m0 + 64 + tx * 4));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* row = g.pq + (static_cast<int64_t>(b) * N + n0 + ty * 4 + i) * M + m0;
+      *reinterpret_cast<float4*>(row + tx * 4) =
+          make_float4(acc[i][0] + b0.x, acc[i][1] + b0.y, acc[i][2] + b0.z, acc[i][3] + b0.w);
+      *reinterpret_cast<float4*>(row + 64 + tx * 4) =
+          make_float4(acc[i][4] + b1.x, acc[i][5] + b1.y, acc[i][6] + b1.z, acc[i][7] + b1.w);
+    }
+  }
+}
+
 // sq (B,N) as in sqnorm_kernel plus the per-cloud maximum (for the certification bound)
 __global__ void sqmax_kernel(const float* __restrict__ sq, int N, float* __restrict__ sqmax) {
   __shared__ float red[32];
@@ -263,6 +358,7 @@ constexpr int TC_FLUSH_EARLY = 10;                    // packed 4-byte entries: 
 constexpr int TC_FLUSH_LATE = 10;                     // list still moves a lot (first tiles), fuller batches afterwards
 constexpr int TC_STAGE_BYTES = TC_PLANES * 2 * TC_MAX_C * 128;   // 32 KB: planes x 2 MN blocks x 64 rows x 128 B
 constexpr int TC_XBLOCK_BYTES = 2 * 16 * 128;                    // 4 KB: one extra K=16 block, 2 MN blocks x 16 rows x 128 B
+constexpr int TC_ISSUE_CHUNK = 2;                                 // 32-column chunk of tile t before which the MMAs of tile t+1 are issued
 
 // Shared memory of one CTA (128 queries of one cloud).  Several CTAs share an SM so that the
 // latency-bound phases of one (exact re-rank, neighbour gather) overlap the streaming phase of another.
@@ -502,7 +598,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
                                         : TC_FLUSH_AT * TC_THREADS * 8u;
 #pragma unroll 1
     for (int cchunk = 0; cchunk < TILE / 32; ++cchunk) {
-      if (cchunk == 2 && more) {
+      if (cchunk == TC_ISSUE_CHUNK && more) {
         // split barrier: everybody arrives (own loads landed and fenced, own reads of the other
         // accumulator retired)
         cp_async_wait_all();
