@@ -105,34 +105,20 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
     t.wide = epilogue_wide_ok(a) ? 1 : 0;
     t.flush_early = TC_FLUSH_EARLY;
     t.flush_late = TC_FLUSH_LATE;
-    if (const char* fe = getenv("DGCN_TC_FLUSH")) {   // tuning hook: "early,late", each in [1, 24]
-      int e1 = 0, l1 = 0;
-      if (sscanf(fe, "%d,%d", &e1, &l1) == 2 && e1 >= 1 && e1 <= 24 && l1 >= 1 && l1 <= 24) {
-        t.flush_early = e1;
-        t.flush_late = l1;
-      }
-    }
-#define DGCN_TC_LAUNCH(KPV)                                                                                   \
-  do {                                                                                                        \
-    t.work_bytes = static_cast<int>(tc_work_bytes(KPV, a.k, t.wide != 0, nch));                               \
-    const size_t smem = static_cast<size_t>(t.work_bytes) + sizeof(TcTail) + 1024;                            \
-    if (N <= 4096) {                                                                                          \
-      DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_tc_kernel<KPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         static_cast<int>(smem)));                                            \
-      knn_tc_kernel<KPV, true><<<grid, TC_THREADS, smem, stream>>>(t);                                        \
-    } else {                                                                                                  \
-      DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_tc_kernel<KPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         static_cast<int>(smem)));                                            \
-      knn_tc_kernel<KPV, false><<<grid, TC_THREADS, smem, stream>>>(t);                                       \
-    }                                                                                                         \
-  } while (0)
     // list length = K + certification margin
     // (a margin of 4 ranks leaves ~1e-5 of the queries of a random 64-d cloud uncertified, 8 ranks none)
-    if (K <= 9) DGCN_TC_LAUNCH(16);
-    else if (K <= 20) DGCN_TC_LAUNCH(28);
-    else if (K <= 32) DGCN_TC_LAUNCH(40);
-    else DGCN_TC_LAUNCH(56);
-#undef DGCN_TC_LAUNCH
+    const int kp = K <= 9 ? 16 : K <= 20 ? 28 : K <= 32 ? 40 : 56;
+    t.work_bytes = static_cast<int>(tc_work_bytes(kp, a.k, t.wide != 0, nch));
+    const size_t smem = static_cast<size_t>(t.work_bytes) + sizeof(TcTail) + 1024;
+    const bool packed = N <= 4096;
+    int rc;
+    switch (kp) {
+      case 16: rc = launch_knn_tc_kp16(packed, t, grid, smem, stream); break;
+      case 28: rc = launch_knn_tc_kp28(packed, t, grid, smem, stream); break;
+      case 40: rc = launch_knn_tc_kp40(packed, t, grid, smem, stream); break;
+      default: rc = launch_knn_tc_kp56(packed, t, grid, smem, stream); break;
+    }
+    if (rc != DGCN_OK) return rc;
     DGCN_LAUNCH_CHECK();
     float* extra = a.epi.partial ? a.epi.partial + n_cta * 2 * a.epi.c_out : nullptr;
     knn_exact_rows_kernel<<<TC_FALLBACK_GRID, 256, 0, stream>>>(a, t.fail_count, t.fail_list, extra);

@@ -57,6 +57,7 @@ __device__ __forceinline__ int keep_rank(const KnnArgs& a, int l) {
 }
 
 // ---- squared norms -----------------------------------------------------------
+#ifndef DGCN_TEMPLATES_ONLY
 __global__ void sqnorm_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C, int N,
                               float* __restrict__ sq) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,6 +71,7 @@ __global__ void sqnorm_kernel(const float* __restrict__ x, int64_t sb, int64_t s
   }
   sq[static_cast<int64_t>(b) * N + n] = s;
 }
+#endif  // DGCN_TEMPLATES_ONLY
 
 // ---- per-query consumers -------------------------------------------------------
 // One warp, one query (cloud b, point q, already-selected neighbour ids sel[0..k)).
@@ -590,6 +592,7 @@ __global__ void __launch_bounds__(NTHREADS, R == 1 ? 2 : 1) knn_small_kernel(con
 
 // ---- large path ------------------------------------------------------------------
 // distance rows of clouds [b0, b0+nb) into ws rows (row = (b-b0)*N + q, ld = ldd)
+#ifndef DGCN_TEMPLATES_ONLY
 __global__ void __launch_bounds__(NTHREADS, 2)
     dist_rows_kernel(const KnnArgs a, int b0, float* __restrict__ drows, int ldd) {
   __shared__ TileSmem ts;
@@ -626,6 +629,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     }
   }
 }
+#endif  // DGCN_TEMPLATES_ONLY
 
 // warp-level bitonic sort of n (power of two) 64-bit keys in shared memory
 __device__ __forceinline__ void warp_bitonic_sort(uint64_t* s, int n, int lane) {
@@ -699,6 +703,7 @@ __device__ __forceinline__ void row_consume(const KnnArgs& a, int b, int q, cons
 // dynamic smem per warp: keys[nkeys] (u32) | sk[KP] (u64) | sel[k] (int)
 // With row_list != null the kernel instead completes the rows listed there (rows the sampled fast
 // kernel could not bound), grid-striding over *row_count entries.
+#ifndef DGCN_TEMPLATES_ONLY
 __global__ void select_rows_kernel(const KnnArgs a, int b0, int nb, const float* __restrict__ drows,
                                    int ldd, int KP, int nkeys, int warps_per_cta, const int* __restrict__ row_list,
                                    const int* __restrict__ row_count) {
@@ -796,11 +801,13 @@ __global__ void select_rows_kernel(const KnnArgs a, int b0, int nb, const float*
   __syncwarp();
   }
 }
+#endif  // DGCN_TEMPLATES_ONLY
 
 // Fast variant: a 128-key sample of the row bounds the K-th distance from above, one pass compacts
 // every key below that bound (in index order) into shared memory, a bitonic sort of the next power of
 // two finishes.  Exact whenever the compacted set holds >= K and <= CAP keys; other rows go to a list
 // that select_rows_kernel completes.  dynamic smem per warp: sk[CAP] (u64) | sel[k] (int).
+#ifndef DGCN_TEMPLATES_ONLY
 __global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const float* __restrict__ drows, int ldd,
                                         int CAP, int sample_rank, int warps_per_cta, int* __restrict__ row_count,
                                         int* __restrict__ row_list) {
@@ -1011,5 +1018,6 @@ __global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const f
   __syncwarp();
   row_consume(a, b, q, nullptr, sel, lane);
 }
+#endif  // DGCN_TEMPLATES_ONLY
 
 }  // namespace dgcn

@@ -151,6 +151,7 @@ constexpr uint32_t kIdescBf16MnMn128x128 =
 // channels >= C are zero.  Four bf16 products hi*hi, hi*mid, mid*hi, mid*mid then reproduce
 // x_i.x_j to ~2^-16 relative - a pre-filter accuracy, the ranking itself is redone in exact fp32.
 constexpr int TC_PLANES = 2;
+#ifndef DGCN_TEMPLATES_ONLY
 __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C, int Cpad, int N,
                                   __nv_bfloat16* __restrict__ planes) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,10 +165,12 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t sb, int64
   base[0] = hi;
   base[plane] = mid;
 }
+#endif  // DGCN_TEMPLATES_ONLY
 
 // One pass over x for everything the tensor-core path needs: sq (B,N) (same FMA chain as sqnorm_kernel),
 // the bf16 planes, the extra operand block sqp that folds -|x_j|^2/2 into the tensor-core product, the node-major copy xt (optional) and the per-cloud max of sq (atomicMax on the bits of
 // a non-negative float; sqmax must be zero-initialised).  Block = 32 points x all channels (C <= 64).
+#ifndef DGCN_TEMPLATES_ONLY
 __global__ void __launch_bounds__(256) tc_prologue_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C,
                                                          int Cpad, int N, float* __restrict__ sq,
                                                          __nv_bfloat16* __restrict__ planes, float* __restrict__ xt,
@@ -216,6 +219,7 @@ __global__ void __launch_bounds__(256) tc_prologue_kernel(const float* __restric
     }
   }
 }
+#endif  // DGCN_TEMPLATES_ONLY
 
 // tc_prologue_kernel fused with the EdgeConv node GEMM PQ[b][n][m] = sum_c x[b][c][n] wk[c][m] + bk[m]
 // (node_pq_kernel's result bit for bit: fp32 FMA chain over c ascending from 0, bias added last), so x is
@@ -227,6 +231,7 @@ struct ProloguePq {
   float* pq;         // (B, N, M)
   int M;
 };
+#ifndef DGCN_TEMPLATES_ONLY
 __global__ void __launch_bounds__(256) tc_prologue_pq_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C,
                                                             int Cpad, int N, float* __restrict__ sq,
                                                             __nv_bfloat16* __restrict__ planes, float* __restrict__ xt,
@@ -311,8 +316,10 @@ __global__ void __launch_bounds__(256) tc_prologue_pq_kernel(const float* __rest
     }
   }
 }
+#endif  // DGCN_TEMPLATES_ONLY
 
 // sq (B,N) as in sqnorm_kernel plus the per-cloud maximum (for the certification bound)
+#ifndef DGCN_TEMPLATES_ONLY
 __global__ void sqmax_kernel(const float* __restrict__ sq, int N, float* __restrict__ sqmax) {
   __shared__ float red[32];
   const int b = blockIdx.x;
@@ -327,6 +334,7 @@ __global__ void sqmax_kernel(const float* __restrict__ sq, int N, float* __restr
     if (threadIdx.x == 0) sqmax[b] = m;
   }
 }
+#endif  // DGCN_TEMPLATES_ONLY
 
 // ---- the tensor-core kernel ------------------------------------------------------------------------
 // 256-bit read-only global load (sm_100: LDG.E.256); p must be 32-byte aligned
@@ -778,6 +786,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
 // chain over channels, the query's channels broadcast from shared memory), each keeps a warp-wide
 // sorted list of its best 64, the 8 lists are merged by one bitonic sort in shared memory, then warp 0
 // runs the per-query consumer.  A lone uncertified query therefore costs ~N/256 candidate rounds, not N/32.
+#ifndef DGCN_TEMPLATES_ONLY
 __global__ void __launch_bounds__(256) knn_exact_rows_kernel(const KnnArgs a, const int* __restrict__ fail_count,
                                                             const int* __restrict__ fail_list,
                                                             float* __restrict__ partial_extra) {
@@ -891,5 +900,27 @@ __global__ void __launch_bounds__(256) knn_exact_rows_kernel(const KnnArgs a, co
     }
   }
 }
+#endif  // DGCN_TEMPLATES_ONLY
+
+// ---- per-list-length launchers --------------------------------------------------------------------------
+// Each list length KP is instantiated in its own translation unit (knn_tc_kp*.cu, compiled in parallel with
+// DGCN_TEMPLATES_ONLY so that the non-template kernels of these headers are not duplicated).
+template <int KP>
+inline int launch_knn_tc_inst(bool packed, const TcArgs& t, dim3 grid, size_t smem, cudaStream_t stream) {
+  if (packed) {
+    DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_tc_kernel<KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    knn_tc_kernel<KP, true><<<grid, TC_THREADS, smem, stream>>>(t);
+  } else {
+    DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_tc_kernel<KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    knn_tc_kernel<KP, false><<<grid, TC_THREADS, smem, stream>>>(t);
+  }
+  return DGCN_OK;
+}
+int launch_knn_tc_kp16(bool packed, const TcArgs& t, dim3 grid, size_t smem, cudaStream_t stream);
+int launch_knn_tc_kp28(bool packed, const TcArgs& t, dim3 grid, size_t smem, cudaStream_t stream);
+int launch_knn_tc_kp40(bool packed, const TcArgs& t, dim3 grid, size_t smem, cudaStream_t stream);
+int launch_knn_tc_kp56(bool packed, const TcArgs& t, dim3 grid, size_t smem, cudaStream_t stream);
 
 }  // namespace dgcn
