@@ -235,7 +235,9 @@ def test_headline_shape_properties():
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 1024, 20, 1), (2, 3, 512, 20, 1), (1, 32, 256, 9, 3), (3, 9, 384, 9, 2),
-                                   (2, 48, 640, 4, 1), (1, 64, 128, 7, 4), (1, 17, 2048, 12, 1)])
+                                   (2, 48, 640, 4, 1), (1, 64, 128, 7, 4), (1, 17, 2048, 12, 1),
+                                   (1, 16, 8192, 10, 1),      # N > 4096: unpacked (key, index) list entries
+                                   (1, 8, 4224, 20, 2)])      # unpacked entries, K = 40 (list length 56)
 def test_tensor_core_prefilter_equals_exact_fp32_path(shape):
     """The tcgen05 pre-filter is certified + re-ranked in exact fp32, so its neighbour lists
     must be IDENTICAL (not just adjudicated-equal) to those of the pure fp32 FMA kernel."""
