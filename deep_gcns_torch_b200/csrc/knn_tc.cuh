@@ -2,26 +2,28 @@
 // N % 128 == 0:  the N x N x C contraction runs on the 5th-gen tensor cores as a CERTIFIED
 // PRE-FILTER, the ranking itself stays exact fp32.
 //
-//   split_kernel      x = hi + mid + lo (three bf16 planes, channel-major like x, channels
-//                     zero-padded to a multiple of 16) - 6 bf16 products hi*hi, hi*mid, mid*hi,
-//                     mid*mid, hi*lo, lo*hi reproduce x_i.x_j to ~2^-22 relative.
-//   knn_tc_kernel     one CTA = 128 queries of a cloud.  Query planes stay resident in shared
-//                     memory; candidate tiles of 128 points stream through a 2-stage cp.async
-//                     ring in the canonical MN-major SWIZZLE_128B layout (x is channel-major =
-//                     MN-major, so no transposition anywhere).  One thread issues the
-//                     tcgen05.mma chain (M=128, N=128, K=16) into one of two TMEM accumulators
-//                     while all 128 threads - thread r owns TMEM lane r = query r - filter the
-//                     other accumulator: approx key = |x_j|^2 - 2*acc against the thread's private
-//                     threshold, survivors go to a private candidate buffer and from there into
-//                     the query's sorted list of the KP best APPROXIMATE keys (no atomics, no
-//                     barriers in the filter).
+//   tc_prologue(_pq)  one pass over x: x = hi + mid (two bf16 planes, channel-major like x, channels
+//                     zero-padded to a multiple of 16; the three products hi*hi, hi*mid, mid*hi
+//                     reproduce x_i.x_j to ~2^-16 relative), |x|^2, the operand block that folds
+//                     -|x_j|^2/2 into the product, the node-major fp32 copy, max |x|^2 (and the
+//                     EdgeConv node GEMM).
+//   knn_tc_kernel     one 128-thread CTA = 128 queries of a cloud, two CTAs per SM.  Query planes stay
+//                     resident in shared memory; candidate tiles of 128 points stream through one
+//                     cp.async stage in the canonical MN-major SWIZZLE_128B layout (x is
+//                     channel-major = MN-major, so no transposition anywhere).  The thread that
+//                     arrives last at the split barrier issues the tcgen05.mma chain (M=128, N=128,
+//                     K=16) of the NEXT tile into one of two TMEM accumulators while all 128 threads -
+//                     thread r owns TMEM lane r = query r - filter the other accumulator against
+//                     the thread's private threshold; survivors go to a private candidate buffer
+//                     and from there into the query's register-resident sorted list of the KP best
+//                     APPROXIMATE keys (no atomics, no CTA barriers in the filter).
 //                     Afterwards each thread re-evaluates its KP candidates with the exact fp32
 //                     FMA chain (same values as knn_small_kernel), sorts them, and certifies:
 //                       exact_K-th + eps < approx_KP-th     (eps = bound on |approx - exact|)
 //                     i.e. nothing outside the list can belong to the true K best.  Certified
 //                     queries run the fused consumer; the others are appended to a fail list.
 //   knn_exact_rows_kernel  completes the (rare) uncertified queries with the exact fp32 brute
-//                     force, one warp per query.
+//                     force, one CTA per query.
 #pragma once
 #include <cuda_bf16.h>
 #include "knn.cuh"
@@ -148,8 +150,9 @@ constexpr uint32_t kIdescBf16MnMn128x128 =
 
 // ---- operand split ----------------------------------------------------------------------------
 // planes (B, TC_PLANES, Cpad, N) bf16: x = hi + mid up to 2^-17 relative (|x - hi - mid| <= 2^-18 |x|);
-// channels >= C are zero.  Four bf16 products hi*hi, hi*mid, mid*hi, mid*mid then reproduce
-// x_i.x_j to ~2^-16 relative - a pre-filter accuracy, the ranking itself is redone in exact fp32.
+// channels >= C are zero.  Three bf16 products hi*hi, hi*mid, mid*hi reproduce x_i.x_j to
+// 3 * 2^-18 relative to |x_i||x_j| (two split residuals + the dropped mid*mid term) - a pre-filter
+// accuracy, the ranking itself is redone in exact fp32.
 constexpr int TC_PLANES = 2;
 #ifndef DGCN_TEMPLATES_ONLY
 __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C, int Cpad, int N,
@@ -485,16 +488,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
   cp_async16_addr(sx_dst, sx_src);
   cp_async_commit();
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-  // One thread issues the 4 x Cpad/16 MMAs of a candidate tile into accumulator `buf` and commits.
+  // One thread issues the 3 x Cpad/16 + 1 MMAs of a candidate tile into accumulator `buf` and commits.
   auto issue_tile = [&](uint32_t tmem_acc) {
     tc_fence_after();
     const uint32_t abase = smem_u32(qstage), bbase = smem_u32(stage);
-    const int pa[4] = {0, 0, 1, 1};   // hi*hi, hi*mid, mid*hi, mid*mid
-    const int pb[4] = {0, 1, 0, 1};
+    const int pa[3] = {0, 0, 1};   // hi*hi, hi*mid, mid*hi  (mid*mid ~ 2^-18 |x_i||x_j| is inside eps)
+    const int pb[3] = {0, 1, 0};
     uint32_t acc = 0;
     for (int kk = 0; kk < Cpad / 16; ++kk) {
 #pragma unroll
-      for (int term = 0; term < 4; ++term) {
+      for (int term = 0; term < 3; ++term) {
         const uint64_t da = umma_desc_mn_sw128(abase + pa[term] * plane_bytes + kk * 2048, Cpad * 128, 1024);
         const uint64_t db = umma_desc_mn_sw128(bbase + pb[term] * plane_bytes + kk * 2048, Cpad * 128, 1024);
         umma_bf16(tmem_acc, da, db, kIdescBf16MnMn128x128, acc);
@@ -749,7 +752,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
     if (ok && cut < INFINITY) {
       const float dk = ordered_to_float(static_cast<uint32_t>(kth >> 32));
       const float smax = __ldg(t.sqmax + b);
-      // |approx - exact fp32| <= eps: 4 bf16 products of the (hi, mid) split (2^-15.5 rel. to |x_i||x_j|),
+      // |approx - exact fp32| <= eps: 3 bf16 products of the (hi, mid) split (2 x 3 x 2^-18 < 2 x 2^-15.5 rel. to |x_i||x_j|),
       // ~4*Cpad fp32 tensor-core accumulations and Cpad FMA-chain roundings (2^-23 each), the -|x_j|^2/2 term
       // accumulated with them (3-term bf16 split, roundings at magnitude <= smax/2) and the final additions (2^-20).
       const float eps = (2.0f * (2.158e-5f + (5.0f * Cpad + 8.0f) * 1.1921e-7f)) * sqrtf(sqq * smax) +
