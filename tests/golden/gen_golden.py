@@ -147,8 +147,31 @@ def sparse_cases(sparse):
              mod.state_dict(), {"y": y, "m": m})
 
 
+def sparse_edge_cases():
+    """gcn_lib/sparse/torch_edge.py (knn='matrix'): flattened, globally numbered kNN graphs of equally
+    sized clouds; regular and stochastic dilation (the latter under a fixed CPU RNG seed)."""
+    te = sys.modules["gcn_lib.sparse.torch_edge"]
+    gen = torch.Generator().manual_seed(3)
+    B, n, C = 4, 96, 7
+    x = torch.randn(B * n, C, generator=gen)
+    batch = torch.arange(B).repeat_interleave(n)
+    outs = {"knn_k9": te.knn_graph_matrix(x, 9, batch),
+            "dilated_k5_d2": te.DilatedKnnGraph(5, 2)(x, batch),
+            "single_cloud_k6_d3": te.DilatedKnnGraph(6, 3)(x[:n], None if False else torch.zeros(n, dtype=torch.long))}
+    sto = te.DilatedKnnGraph(5, 3, True, 1.0).train()
+    torch.manual_seed(11)
+    outs["stochastic_k5_d3_seed11"] = sto(x, batch)
+    full = te.knn_graph_matrix(x, 15, batch)
+    dil = te.Dilated(5, 3, True, 1.0).train()
+    torch.manual_seed(12)
+    outs["dilated_module_seed12"] = dil(full)
+    save("spgraph_knn_matrix", dict(B=B, n=n, C=C), {"x": x, "batch": batch.to(torch.int32)}, {},
+         {k: v.to(torch.int32) for k, v in outs.items()})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     dense, sparse = ref_shims.load_reference()
     dense_cases(dense)
     sparse_cases(sparse)
+    sparse_edge_cases()

@@ -154,3 +154,43 @@ def test_power_law_graph_hub_rows():
         with_hubs = _native.genconv_aggregate(x.cuda(), x.cuda(), csr, prm)
         no_hubs = _native.genconv_aggregate(x.cuda(), x.cuda(), csr[:3], prm)
         torch.testing.assert_close(with_hubs, no_hubs, rtol=1e-4, atol=1e-5)
+
+
+def test_sparse_graph_builders_match_golden_and_oracle():
+    """gcn_lib.sparse.torch_edge (knn='matrix'): flattened, globally numbered kNN graphs from the dense
+    selection kernels - bit-exact against the reference's vectors up to fp32 near-ties (adjudicated
+    in fp64), regular and stochastic dilation under the reference's RNG consumption."""
+    from deep_gcns_torch_b200.gcn_lib import sparse as S
+    from oracle import dense as od
+    c = gu.load("spgraph_knn_matrix")
+    x, batch = c.ins["x"], c.ins["batch"].long()
+    n, B = c.meta["n"], c.meta["B"]
+    xc, bc = x.cuda(), batch.cuda()
+
+    def check(got, ref, k, xs, nb):
+        assert got.shape == ref.shape and got.dtype == torch.int64
+        assert torch.equal(got[1].cpu(), ref[1])
+        npts = xs.shape[0] // nb
+        xb = xs.reshape(nb, npts, -1).transpose(1, 2).unsqueeze(-1)
+        off = torch.arange(0, nb * npts, npts).view(nb, 1, 1)
+        n_bad, n_unexplained = od.knn_mismatch_report(xb, got[0].cpu().view(nb, npts, k) - off,
+                                                      ref[0].view(nb, npts, k) - off)
+        assert n_unexplained == 0 and n_bad <= 1e-3 * got[0].numel()
+
+    check(S.knn_graph_matrix(xc, 9, bc), c.outs["knn_k9"].long(), 9, x, B)
+    nn_idx, centre = S.knn_matrix(xc, 9, bc)
+    assert nn_idx.shape == (1, B * n * 9) and torch.equal(centre[0].cpu(), c.outs["knn_k9"][1].long())
+    # dilation happens inside the selection kernel: must equal striding the full list
+    full = S.knn_graph_matrix(xc, 10, bc)
+    got = S.DilatedKnnGraph(5, 2)(xc, bc)
+    assert torch.equal(got, full[:, ::2])
+    assert (got.cpu() == c.outs["dilated_k5_d2"].long()).float().mean() > 0.999
+    single = S.DilatedKnnGraph(6, 3)(xc[:n], torch.zeros(n, dtype=torch.long, device="cuda"))
+    assert (single.cpu() == c.outs["single_cloud_k6_d3"].long()).float().mean() > 0.999
+    # stochastic dilation: same CPU generator draws, same random columns as the reference
+    sto = S.DilatedKnnGraph(5, 3, True, 1.0).train()
+    torch.manual_seed(11)
+    got = sto(xc, bc)
+    assert (got.cpu() == c.outs["stochastic_k5_d3_seed11"].long()).float().mean() > 0.999
+    with pytest.raises(NotImplementedError):
+        S.DilatedKnnGraph(5, 1, knn="cluster")
