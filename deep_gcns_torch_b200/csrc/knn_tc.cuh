@@ -32,7 +32,6 @@ namespace dgcn {
 
 constexpr int TC_MAX_C = 64;
 constexpr int TC_K_MAX = 48;
-constexpr int TC_CAP = 8;          // private candidate buffer entries per query
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -154,25 +153,11 @@ constexpr uint32_t kIdescBf16MnMn128x128 =
 // 3 * 2^-18 relative to |x_i||x_j| (two split residuals + the dropped mid*mid term) - a pre-filter
 // accuracy, the ranking itself is redone in exact fp32.
 constexpr int TC_PLANES = 2;
-#ifndef DGCN_TEMPLATES_ONLY
-__global__ void split_bf16_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C, int Cpad, int N,
-                                  __nv_bfloat16* __restrict__ planes) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = blockIdx.y, b = blockIdx.z;
-  if (n >= N) return;
-  float v = c < C ? __ldg(x + b * sb + c * sc + n) : 0.f;
-  __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  __nv_bfloat16 mid = __float2bfloat16_rn(v - __bfloat162float(hi));
-  const int64_t plane = static_cast<int64_t>(Cpad) * N;
-  __nv_bfloat16* base = planes + (static_cast<int64_t>(b) * TC_PLANES) * plane + static_cast<int64_t>(c) * N + n;
-  base[0] = hi;
-  base[plane] = mid;
-}
-#endif  // DGCN_TEMPLATES_ONLY
 
 // One pass over x for everything the tensor-core path needs: sq (B,N) (same FMA chain as sqnorm_kernel),
-// the bf16 planes, the extra operand block sqp that folds -|x_j|^2/2 into the tensor-core product, the node-major copy xt (optional) and the per-cloud max of sq (atomicMax on the bits of
-// a non-negative float; sqmax must be zero-initialised).  Block = 32 points x all channels (C <= 64).
+// the bf16 planes, the extra operand block sqp that folds -|x_j|^2/2 into the tensor-core product, the
+// node-major copy xt (optional) and the per-cloud max of sq (atomicMax on the bits of a non-negative
+// float; sqmax must be zero-initialised).  Block = 32 points x all channels (C <= 64).
 #ifndef DGCN_TEMPLATES_ONLY
 __global__ void __launch_bounds__(256) tc_prologue_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C,
                                                          int Cpad, int N, float* __restrict__ sq,
@@ -321,23 +306,7 @@ __global__ void __launch_bounds__(256) tc_prologue_pq_kernel(const float* __rest
 }
 #endif  // DGCN_TEMPLATES_ONLY
 
-// sq (B,N) as in sqnorm_kernel plus the per-cloud maximum (for the certification bound)
-#ifndef DGCN_TEMPLATES_ONLY
-__global__ void sqmax_kernel(const float* __restrict__ sq, int N, float* __restrict__ sqmax) {
-  __shared__ float red[32];
-  const int b = blockIdx.x;
-  float m = 0.f;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmaxf(m, sq[static_cast<int64_t>(b) * N + i]);
-  m = warp_max(m);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-    m = warp_max(m);
-    if (threadIdx.x == 0) sqmax[b] = m;
-  }
-}
-#endif  // DGCN_TEMPLATES_ONLY
+
 
 // ---- the tensor-core kernel ------------------------------------------------------------------------
 // 256-bit read-only global load (sm_100: LDG.E.256); p must be 32-byte aligned
