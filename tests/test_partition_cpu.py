@@ -61,3 +61,41 @@ def test_row_ranges_cover():
         r = row_ranges(n, w)
         assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
         assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+
+
+def _dense_worker(rank, world, port, out):
+    """Dense path: the cloud batch is sharded, no data-path collective.  With the oracle
+    standing in for the CUDA layer, the all-gathered shard outputs must equal the full-batch result
+    bit for bit (clouds never interact), and the bench's max-over-ranks time reduction must agree."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deep_gcns_torch_b200.partition import row_ranges
+    from oracle import dense as od
+    g = torch.Generator().manual_seed(0)
+    B, C, N, k, d = 6, 8, 96, 5, 2
+    x = torch.randn(B, C, N, 1, generator=g)
+    torch.manual_seed(1)
+    conv = torch.nn.Conv2d(2 * C, 10, 1)
+    p = {"weight": conv.weight.detach(), "bias": conv.bias.detach()}
+    lo, hi = row_ranges(B, world)[rank]
+    y_loc = od.dyn_conv(x[lo:hi], p, k, d, "edge", "relu", None)
+    ei_loc = od.dilated_knn_graph(x[lo:hi], k, d)
+    ys = [torch.empty_like(y_loc) for _ in range(world)]
+    eis = [torch.empty_like(ei_loc) for _ in range(world)]
+    dist.all_gather(ys, y_loc)
+    dist.all_gather(eis, ei_loc.contiguous())
+    assert torch.equal(torch.cat(ys, 0), od.dyn_conv(x, p, k, d, "edge", "relu", None))
+    assert torch.equal(torch.cat(eis, 1), od.dilated_knn_graph(x, k, d))
+    t = torch.tensor([1.0 + rank, 2.0 - rank], dtype=torch.float64)      # per-rank "timings"
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out[rank] = t.tolist()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dense_batch_sharding_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dense_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0] == out[1] == [2.0, 2.0]
