@@ -1,5 +1,4 @@
 """GENConv - API of the reference's gcn_lib/sparse/torch_vertex.py:12-88."""
-import torch
 from torch import nn
 
 from .torch_nn import MLP, BondEncoder
