@@ -129,3 +129,37 @@ def test_signatures_match_live_reference():
     theirs = ns2["DenseDeepGCN"](opt)
     assert list(mine.state_dict().keys()) == list(theirs.state_dict().keys())
     mine.load_state_dict(theirs.state_dict(), strict=True)
+
+
+def test_bench_line_carries_every_contract_key():
+    """Static check of bench.py's JSON line (no GPU): the dict literal assembled in run_native, evaluated
+    with stand-in measurements, has every key of the bench contract and consistent derived values."""
+    import ast
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "bench.py")
+    tree = ast.parse(open(path).read())
+    g = {"__file__": path, "__name__": "bench_static"}
+    top = [n for n in tree.body if isinstance(n, (ast.Assign, ast.Import, ast.ImportFrom))]
+    exec(compile(ast.Module(top, []), path, "exec"), g)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "run_native")
+    lit = next(n.value for n in ast.walk(fn) if isinstance(n, ast.Assign) and isinstance(n.targets[0], ast.Name)
+               and n.targets[0].id == "out" and isinstance(n.value, ast.Dict))
+
+    class Args:
+        steps, warmup = 20, 1
+
+    loc = dict(world=2, args=Args, ms=11.4, ms_e2e=12.7, clk={"sm_mhz": 1965.0}, achieved=66.0, peak=6563.9,
+               traffic=72000000, peak_src="measured", kernel_ms=0.507, tensor_peak=1691.8, fp32_peak=74.45, sm_max=1965.0)
+    out = eval(compile(ast.Expression(lit), path, "eval"), g, loc)
+    json.dumps(out)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert key in out, key
+    assert out["warmup"] >= 3 and out["n_gpus"] == 2 and out["scaling"] == "weak" and out["vs_baseline"] is None
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(out["roofline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(out["e2e"])
+    assert "workload" in out["config"] and "model" not in out["config"]
+    edges = 16 * 4096 * 20
+    assert abs(out["value"] - edges * 2 * 20 / 11.4e-3) < 1.0          # whole-job aggregate over both ranks
+    assert out["gpu_launches"] > 0
