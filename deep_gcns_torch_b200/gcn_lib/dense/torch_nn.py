@@ -11,77 +11,77 @@ from torch import nn
 
 __all__ = ["act_layer", "norm_layer", "MLP", "BasicConv", "batched_index_select"]
 
+# name -> factory(inplace, negative slope, PReLU parameter count)          (torch_nn.py:9-21)
+_ACTIVATIONS = {
+    "relu": lambda inplace, slope, n: nn.ReLU(inplace),
+    "leakyrelu": lambda inplace, slope, n: nn.LeakyReLU(slope, inplace),
+    "prelu": lambda inplace, slope, n: nn.PReLU(num_parameters=n, init=slope),
+}
+# name -> factory(channels)                                                 (torch_nn.py:24-33)
+_NORMS = {
+    "batch": lambda nc: nn.BatchNorm2d(nc, affine=True),
+    "instance": lambda nc: nn.InstanceNorm2d(nc, affine=False),
+}
+
+
+def _lookup(table, name, what):
+    try:
+        return table[name.lower()]
+    except KeyError:
+        raise NotImplementedError("%s layer [%s] is not found" % (what, name.lower())) from None
+
 
 def act_layer(act, inplace=False, neg_slope=0.2, n_prelu=1):
-    """torch_nn.py:9-21."""
-    kind = act.lower()
-    if kind == "relu":
-        return nn.ReLU(inplace)
-    if kind == "leakyrelu":
-        return nn.LeakyReLU(neg_slope, inplace)
-    if kind == "prelu":
-        return nn.PReLU(num_parameters=n_prelu, init=neg_slope)
-    raise NotImplementedError("activation layer [%s] is not found" % kind)
+    return _lookup(_ACTIVATIONS, act, "activation")(inplace, neg_slope, n_prelu)
 
 
 def norm_layer(norm, nc):
-    """torch_nn.py:24-33."""
-    kind = norm.lower()
-    if kind == "batch":
-        return nn.BatchNorm2d(nc, affine=True)
-    if kind == "instance":
-        return nn.InstanceNorm2d(nc, affine=False)
-    raise NotImplementedError("normalization layer [%s] is not found" % kind)
+    return _lookup(_NORMS, norm, "normalization")(nc)
 
 
-def _wanted(name):
-    return name is not None and name.lower() != "none"
+def _named(option):
+    return option is not None and option.lower() != "none"
+
+
+def _stages(channels, unit, act, norm, drop=0.):
+    """unit(c_in, c_out) -> act -> norm(channels[-1]) [-> Dropout2d] for consecutive channel pairs, in
+    the reference's module order (it fixes the state_dict indices and the order of RNG draws)."""
+    for c_in, c_out in zip(channels[:-1], channels[1:]):
+        yield unit(c_in, c_out)
+        if _named(act):
+            yield act_layer(act)
+        if _named(norm):
+            yield norm_layer(norm, channels[-1])
+        if drop > 0:
+            yield nn.Dropout2d(drop)
 
 
 class MLP(nn.Sequential):
-    """torch_nn.py:36-45 (Linear -> act -> norm); not used by the hot path."""
+    """torch_nn.py:36-45; not used by the hot path."""
 
     def __init__(self, channels, act="relu", norm=None, bias=True):
-        layers = []
-        for c_in, c_out in zip(channels[:-1], channels[1:]):
-            layers.append(nn.Linear(c_in, c_out, bias))
-            if _wanted(act):
-                layers.append(act_layer(act))
-            if _wanted(norm):
-                layers.append(norm_layer(norm, channels[-1]))
-        super().__init__(*layers)
+        super().__init__(*_stages(channels, lambda i, o: nn.Linear(i, o, bias), act, norm))
 
 
 class BasicConv(nn.Sequential):
     """torch_nn.py:48-72."""
 
     def __init__(self, channels, act="relu", norm=None, bias=True, drop=0.):
-        layers = []
-        for c_in, c_out in zip(channels[:-1], channels[1:]):
-            layers.append(nn.Conv2d(c_in, c_out, 1, bias=bias))
-            if _wanted(act):
-                layers.append(act_layer(act))
-            if _wanted(norm):
-                layers.append(norm_layer(norm, channels[-1]))
-            if drop > 0:
-                layers.append(nn.Dropout2d(drop))
-        super().__init__(*layers)
+        super().__init__(*_stages(channels, lambda i, o: nn.Conv2d(i, o, 1, bias=bias), act, norm, drop))
         self.reset_parameters()
 
     def reset_parameters(self):
-        for m in self.modules():
-            if isinstance(m, nn.Conv2d):
-                nn.init.kaiming_normal_(m.weight)
-                if m.bias is not None:
-                    nn.init.zeros_(m.bias)
-            elif isinstance(m, nn.BatchNorm2d):
-                m.weight.data.fill_(1)
-                m.bias.data.zero_()
-            elif isinstance(m, nn.InstanceNorm2d):
-                # the reference dereferences the (absent) affine weight here and raises
-                # AttributeError (torch_nn.py:71): 'instance' cannot be built through BasicConv.
-                m.weight.data.fill_(1)
-                m.bias.data.zero_()
+        """Kaiming-normal 1x1 weights, zero biases, unit / zero affine norms (torch_nn.py:64-72)."""
+        for layer in self.modules():
+            if isinstance(layer, nn.Conv2d):
+                nn.init.kaiming_normal_(layer.weight)
+                if layer.bias is not None:
+                    nn.init.zeros_(layer.bias)
+            elif isinstance(layer, (nn.BatchNorm2d, nn.InstanceNorm2d)):
+                # InstanceNorm2d(affine=False) has no weight: like the reference (torch_nn.py:71) this
+                # raises AttributeError, i.e. 'instance' cannot be built through BasicConv.
+                layer.weight.data.fill_(1)
+                layer.bias.data.zero_()
 
 
 def batched_index_select(x, idx):
