@@ -230,6 +230,7 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL's version banner)
         dist.init_process_group("nccl", device_id=dev)
     from deep_gcns_torch_b200 import _native
     from deep_gcns_torch_b200.gcn_lib import dense as D
@@ -353,20 +354,21 @@ def run_native(args):
                    "fp32_fma_peak_tflops_at_sampled_clock": fp32_peak,
                    "frac_of_fp32_fma_peak": EDGES_PER_STEP * FLOPS_PER_EDGE / (kernel_ms * 1e-3) / 1e12 / fp32_peak},
     }
-    # ---- CPU baseline: the reference algorithm on this box's host cores, bounded sample ----
-    threads = len(os.sched_getaffinity(0))
-    run = oracle_layer(threads)
-    xc = cpu_sample()
-    run(xc)
-    reps, t0 = 0, time.perf_counter()
-    while reps < 3 or (time.perf_counter() - t0 < args.cpu_seconds and reps < 50):
+    # ---- CPU baseline: the reference algorithm on this box's host cores, bounded sample (N=1 only) ----
+    if world == 1:
+        threads = len(os.sched_getaffinity(0))
+        run = oracle_layer(threads)
+        xc = cpu_sample()
         run(xc)
-        reps += 1
-    dt = time.perf_counter() - t0
-    out["cpu_baseline"] = {"value": xc.shape[0] * N * K_NEIGH * reps / dt, "unit": "edges/s", "cores": threads,
-                           "kind": "port",
-                           "sample": "oracle port of the reference layer on %d of the %d clouds, %d repeats, %.1f s"
-                                     % (xc.shape[0], B, reps, dt)}
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < args.cpu_seconds and reps < 50):
+            run(xc)
+            reps += 1
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": xc.shape[0] * N * K_NEIGH * reps / dt, "unit": "edges/s", "cores": threads,
+                               "kind": "port",
+                               "sample": "oracle port of the reference layer on %d of the %d clouds, %d repeats, %.1f s"
+                                         % (xc.shape[0], B, reps, dt)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
