@@ -33,7 +33,12 @@ class BasicConvC(ctypes.Structure):
 
 
 class DilationC(ctypes.Structure):
-    _fields_ = [("k", c_i64), ("dilation", c_i64), ("cols_host", ctypes.POINTER(c_i32))]
+    _fields_ = [("k", c_i64), ("dilation", c_i64), ("cols_host", ctypes.POINTER(c_i32)), ("flags", c_i32),
+                ("reserved", c_i32)]
+
+
+KNN_EXACT_FP32 = 1         # dgcn_knn_flags
+_knn_flags = threading.local()
 
 
 class CsrHubsC(ctypes.Structure):
@@ -100,8 +105,6 @@ def _declare(lib):
     lib.dgcn_debug_kernel_timing_read.restype = ctypes.c_int
     lib.dgcn_debug_kernel_timing_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double),
                                                   ctypes.POINTER(c_i64)]
-    lib.dgcn_debug_set_knn_path.restype = ctypes.c_int
-    lib.dgcn_debug_set_knn_path.argtypes = [c_i32]
     lib.dgcn_gather_rows.restype = ctypes.c_int
     lib.dgcn_gather_rows.argtypes = [vp, c_i64, vp, c_i64, vp, vp]
 
@@ -166,6 +169,7 @@ def _dense_view(x):
 def _dilation(k, dilation, cols):
     d = DilationC()
     d.k, d.dilation = int(k), int(dilation)
+    d.flags, d.reserved = getattr(_knn_flags, "value", 0), 0
     keep = None
     if cols is not None:
         arr = (c_i32 * int(k))(*[int(c) for c in cols])
@@ -313,8 +317,7 @@ def graph_conv_backward(conv, x, prm, grad_out, edge_index=None, nbr=None, need_
              "bn_weight": f(c_out) if prm.norm != NORM_NONE else None,
              "bn_bias": f(c_out) if prm.norm != NORM_NONE else None,
              "prelu": f(1) if prm.prelu_weight is not None else None}
-        ws = _workspace(l.dgcn_graph_conv_backward_workspace_bytes(CONV[conv], B, C, c_out, N, k) + 8 * c_out + 256,
-                        dev)
+        ws = _workspace(l.dgcn_graph_conv_backward_workspace_bytes(CONV[conv], B, C, c_out, N, k), dev)
         rc = l.dgcn_graph_conv_backward(CONV[conv], _ptr(x3), B, C, N, sb, sc, _ptr(edge_index), _ptr(nbr), k,
                                         ctypes.byref(cs), c_out, _ptr(go), _ptr(g["x"]), _ptr(g["weight"]),
                                         _ptr(g["bias"]), _ptr(g["bn_weight"]), _ptr(g["bn_bias"]), _ptr(g["prelu"]),
@@ -451,5 +454,7 @@ def kernel_timing_read(tag):
 
 
 def set_knn_path(path):
-    """'tc' (tcgen05 pre-filter + exact re-rank), 'ffma' (fp32 FMA kernel only) or 'auto'."""
-    return lib().dgcn_debug_set_knn_path({"ffma": 0, "tc": 1, "auto": -1}[path])
+    """A/B switch for tests and measurements: 'ffma' makes the calls of THIS thread pass
+    DGCN_KNN_EXACT_FP32 (fp32 FMA selection kernels only); 'tc' / 'auto' = the default routing
+    (tcgen05 pre-filter + exact re-rank where the shape allows).  The library holds no state."""
+    _knn_flags.value = {"ffma": KNN_EXACT_FP32, "tc": 0, "auto": 0}[path]

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <atomic>
 
 #include "../../include/dgcn.h"
 
@@ -27,6 +28,22 @@ void set_last_cuda_error(cudaError_t e, const char* file, int line);
       ::dgcn::set_last_cuda_error(e__, __FILE__, __LINE__);        \
       return DGCN_ERR_CUDA;                                        \
     }                                                              \
+  } while (0)
+
+// Dynamic shared memory opt-in, once per (call site, device): the attribute is sticky, so it is set on
+// first use (or when a larger size is asked for) instead of before every launch.  The table is a
+// write-once cache of what the driver already knows, not program state.
+#define DGCN_ENSURE_SMEM(kernel, bytes)                                                              \
+  do {                                                                                               \
+    static std::atomic<int> smem_set__[64];                                                          \
+    int dev__ = 0;                                                                                   \
+    DGCN_CUDA_TRY(cudaGetDevice(&dev__));                                                            \
+    const int want__ = static_cast<int>(bytes);                                                      \
+    const bool slot__ = dev__ >= 0 && dev__ < 64;                                                    \
+    if (!slot__ || smem_set__[dev__].load(std::memory_order_relaxed) < want__) {                     \
+      DGCN_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want__)); \
+      if (slot__) smem_set__[dev__].store(want__, std::memory_order_relaxed);                        \
+    }                                                                                                \
   } while (0)
 
 // Optional event bracket around a path's dominant kernel (see dgcn_debug_kernel_timing).

@@ -364,7 +364,7 @@ __global__ void mr_scatter_kernel(const float* __restrict__ dxcat, const int32_t
 }
 
 struct BwdPlan {
-  size_t wk, bk, pq, dpq, partial, sums, dwcat, xt, r, argj, argi, z, dxcat;
+  size_t wk, bk, pq, dpq, partial, sums, dwcat, sf, xt, r, argj, argi, z, dxcat;
   int64_t n_partial;
 };
 static BwdPlan bwd_plan(int conv, int64_t B, int64_t ci, int64_t co, int64_t N) {
@@ -373,6 +373,7 @@ static BwdPlan bwd_plan(int conv, int64_t B, int64_t ci, int64_t co, int64_t N) 
   if (conv == DGCN_CONV_EDGE) {
     p.wk = ci * 2 * co; p.bk = 2 * co; p.pq = B * N * 2 * co; p.dpq = B * 2 * co * N;
     p.n_partial = ceil_div(N, 32) * B; p.partial = p.n_partial * 3 * co; p.dwcat = 2 * co * ci;
+    p.sf = 2 * co;   // train-mode BN: (dbeta, dgamma) as floats for pass B
   } else {
     p.wk = 2 * ci * co; p.xt = B * N * ci; p.r = B * ci * N; p.argj = B * ci * N; p.argi = B * ci * N;
     p.z = B * co * N; p.dxcat = B * 2 * ci * N;
@@ -382,7 +383,7 @@ static BwdPlan bwd_plan(int conv, int64_t B, int64_t ci, int64_t co, int64_t N) 
 }
 static size_t bwd_plan_bytes(const BwdPlan& p) {
   size_t b = 0;
-  for (size_t v : {p.wk, p.bk, p.pq, p.dpq, p.partial, p.sums, p.dwcat, p.xt, p.r, p.argj, p.argi, p.z, p.dxcat})
+  for (size_t v : {p.wk, p.bk, p.pq, p.dpq, p.partial, p.sums, p.dwcat, p.sf, p.xt, p.r, p.argj, p.argi, p.z, p.dxcat})
     b += align_up(v * 4, 256);
   return b + 512;
 }
@@ -452,7 +453,7 @@ int dgcn_graph_conv_backward(int32_t conv, const float* x, int64_t B, int64_t ci
     EdgeBwdArgs g1 = g;
     if (train) {
       // pass B wants (dbeta, dgamma) as float[2][co]: finish_param_grads_kernel does the conversion
-      float* sf = ws.take<float>(static_cast<size_t>(2 * co));
+      float* sf = ws.take<float>(pl.sf);
       if (!ws.ok) return DGCN_ERR_WORKSPACE;
       finish_param_grads_kernel<<<static_cast<unsigned>(ceil_div(co, 128)), 128, 0, stream>>>(sums, ico, 0, sf + co, sf,
                                                                                            nullptr);

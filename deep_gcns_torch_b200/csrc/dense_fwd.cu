@@ -27,14 +27,6 @@ constexpr int TC_FALLBACK_GRID = 148;  // CTAs of the exact completion kernel (o
 static bool tc_shape_ok(int64_t C, int64_t N, int64_t K) {
   return K <= TC_K_MAX && C <= TC_MAX_C && N >= TILE && (N % TILE) == 0;
 }
-static int g_knn_path = -1;   // -1: from env DGCN_KNN_PATH (default tensor cores), 0: fp32 FMA only, 1: tensor cores
-static bool tc_enabled() {
-  if (g_knn_path < 0) {
-    const char* v = getenv("DGCN_KNN_PATH");
-    g_knn_path = (v && strcmp(v, "ffma") == 0) ? 0 : 1;
-  }
-  return g_knn_path == 1;
-}
 
 size_t knn_workspace_bytes(int64_t B, int64_t C, int64_t N, int64_t K) {
   size_t bytes = align_up(static_cast<size_t>(B) * N * 4, 256);
@@ -76,8 +68,7 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
   // sq, bf16 planes, node-major copy and max |x|^2 in one pass over x (sq overwrites what the caller computed)
   if (pqf) {   // the EdgeConv node GEMM rides on the same pass over x
     const size_t smem = (static_cast<size_t>(TC_MAX_C) * 68 + static_cast<size_t>(C) * pqf->M) * 4;
-    DGCN_CUDA_TRY(cudaFuncSetAttribute(tc_prologue_pq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
+    DGCN_ENSURE_SMEM((tc_prologue_pq_kernel), smem);
     tc_prologue_pq_kernel<<<dim3(N / 64, B), 256, smem, stream>>>(a.x, a.sb, a.sc, C, cpad, N, const_cast<float*>(a.sq),
                                                                   planes, xt ? nullptr : xt_own, sqmax, sqp, *pqf);
   } else {
@@ -133,7 +124,7 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
 // true when launch_knn will take the tensor-core path for these arguments
 static bool knn_takes_tc(const KnnArgs& a) {
   const bool train_wide = a.epi.mode == EPI_EDGE && a.epi.norm == DGCN_NORM_BATCH_TRAIN && a.epi.c_out > 128;
-  return tc_enabled() && tc_shape_ok(a.C, a.N, a.K) && a.k <= SEL_LD && !train_wide;
+  return !a.exact_fp32 && tc_shape_ok(a.C, a.N, a.K) && a.k <= SEL_LD && !train_wide;
 }
 // the fused prologue can also produce PQ (EdgeConv): channel / output counts it supports
 static bool prologue_pq_ok(const KnnArgs& a, int64_t M) {
@@ -157,8 +148,7 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
   if (n_partial) *n_partial = K <= SMALL_K_MAX ? static_cast<int64_t>(grid.x) * grid.y : static_cast<int64_t>(B) * N;
   if (K <= 32) {
     const size_t smem = sizeof(SmallSmem<1>);
-    DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
+    DGCN_ENSURE_SMEM((knn_small_kernel<1>), smem);
     {
       KernelTimer timer(stream, "knn");
       knn_small_kernel<1><<<grid, NTHREADS, smem, stream>>>(a);
@@ -177,8 +167,7 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
   if (warps < 1) return DGCN_ERR_UNSUPPORTED;   // a single row does not fit in shared memory
   if (warps > 4) warps = 4;
   const size_t smem = per_warp * warps;
-  DGCN_CUDA_TRY(cudaFuncSetAttribute(select_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
+  DGCN_ENSURE_SMEM((select_rows_kernel), smem);
   // sampled fast select: bound = sample_rank-th of 128 samples (mean + 2.5 sigma + 2 of the K/N quantile)
   const double pq = static_cast<double>(K) / N;
   int sample_rank = static_cast<int>(128.0 * pq + 2.5 * sqrt(128.0 * pq * (1.0 - pq)) + 2.0) + 1;
@@ -202,8 +191,7 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
   if (fast) {
     rowlist = ws.take<int>(static_cast<size_t>(nbmax) * N + 64);
     if (!ws.ok) return DGCN_ERR_WORKSPACE;
-    DGCN_CUDA_TRY(cudaFuncSetAttribute(select_rows_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem_f)));
+    DGCN_ENSURE_SMEM((select_rows_fast_kernel), smem_f);
   }
   KernelTimer timer(stream, "knn");
   for (int b0 = 0; b0 < B; b0 += nbmax) {
@@ -240,6 +228,7 @@ int fill_knn_args(KnnArgs& a, const float* x, int64_t B, int64_t C, int64_t N, i
   a.sq = nullptr;
   a.K = static_cast<int>(K); a.k = static_cast<int>(dil->k); a.dilation = static_cast<int>(dil->dilation);
   a.exclude_self = exclude_self ? 1 : 0;
+  a.exact_fp32 = (dil->flags & DGCN_KNN_EXACT_FP32) ? 1 : 0;
   a.has_cols = dil->cols_host ? 1 : 0;
   for (int l = 0; l < MAX_KEEP; ++l) a.cols[l] = 0;
   if (dil->cols_host) {
@@ -689,12 +678,6 @@ static int conv_forward(int conv, const float* x, int64_t B, int64_t ci, int64_t
 using namespace dgcn;
 
 extern "C" {
-
-int dgcn_debug_set_knn_path(int32_t path) {
-  int old = dgcn::g_knn_path;
-  dgcn::g_knn_path = path;
-  return old;
-}
 
 size_t dgcn_knn_graph_workspace_bytes(int64_t B, int64_t C, int64_t N, int64_t K) {
   return knn_workspace_bytes(B, C, N, K);

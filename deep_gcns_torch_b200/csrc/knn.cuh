@@ -48,6 +48,7 @@ struct KnnArgs {
   const float* x; int64_t sb, sc; int B, C, N; int vec;
   const float* sq;          // (B,N) squared norms
   int K, k, dilation, has_cols, exclude_self;
+  int exact_fp32;           // dgcn_dilation.flags & DGCN_KNN_EXACT_FP32 (host-side routing only)
   int cols[MAX_KEEP];
   Epilogue epi;
 };

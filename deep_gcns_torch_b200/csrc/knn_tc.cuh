@@ -880,12 +880,10 @@ __global__ void __launch_bounds__(256) knn_exact_rows_kernel(const KnnArgs a, co
 template <int KP>
 inline int launch_knn_tc_inst(bool packed, const TcArgs& t, dim3 grid, size_t smem, cudaStream_t stream) {
   if (packed) {
-    DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_tc_kernel<KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
+    DGCN_ENSURE_SMEM((knn_tc_kernel<KP, true>), smem);
     knn_tc_kernel<KP, true><<<grid, TC_THREADS, smem, stream>>>(t);
   } else {
-    DGCN_CUDA_TRY(cudaFuncSetAttribute(knn_tc_kernel<KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
+    DGCN_ENSURE_SMEM((knn_tc_kernel<KP, false>), smem);
     knn_tc_kernel<KP, false><<<grid, TC_THREADS, smem, stream>>>(t);
   }
   return DGCN_OK;

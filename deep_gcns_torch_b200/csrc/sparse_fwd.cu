@@ -337,15 +337,9 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, int C, const int
   }
 }
 
-}  // namespace dgcn
-
-using namespace dgcn;
-
-extern "C" {
-
 // Work list of the long rows: per row ceil(deg / seg_edges) (row, segment) items and one
 // (row, first item, #segments) triple.  Order is arbitrary; every entry is processed independently.
-__global__ void hub_rows_kernel(const int32_t* __restrict__ rowptr, int N, int min_degree, int seg_edges,
+static __global__ void hub_rows_kernel(const int32_t* __restrict__ rowptr, int N, int min_degree, int seg_edges,
                                 int32_t* __restrict__ items, int32_t* __restrict__ item_count,
                                 int32_t* __restrict__ rows, int32_t* __restrict__ row_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -364,7 +358,13 @@ __global__ void hub_rows_kernel(const int32_t* __restrict__ rowptr, int N, int m
   rows[3 * r + 2] = nseg;
 }
 
-extern "C" int dgcn_csr_hub_rows(const int32_t* rowptr, int64_t N, int64_t E, int32_t min_degree, int32_t seg_edges,
+}  // namespace dgcn
+
+using namespace dgcn;
+
+extern "C" {
+
+int dgcn_csr_hub_rows(const int32_t* rowptr, int64_t N, int64_t E, int32_t min_degree, int32_t seg_edges,
                                  int32_t* items, int32_t* rows, int32_t* counts, dgcn_stream_t stream) {
   if (!rowptr || !items || !rows || !counts || N <= 0 || min_degree <= 0 || seg_edges <= 0) return DGCN_ERR_BAD_ARG;
   (void)E;
@@ -418,8 +418,9 @@ int dgcn_genconv_aggregate(const float* x_src, const float* x_dst, int64_t N, in
 }
 
 int dgcn_gather_rows(const float* x, int64_t C, const int32_t* rows, int64_t R, float* out, dgcn_stream_t stream) {
-  if (!x || !rows || !out || C <= 0 || R < 0) return DGCN_ERR_BAD_ARG;
-  if (R == 0) return DGCN_OK;
+  if (C <= 0 || R < 0) return DGCN_ERR_BAD_ARG;
+  if (R == 0) return DGCN_OK;   // an empty halo list is legal (its tensors have null data pointers)
+  if (!x || !rows || !out) return DGCN_ERR_BAD_ARG;
   gather_rows_kernel<<<static_cast<unsigned>(ceil_div(R, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, static_cast<int>(C), rows, R, out);
   DGCN_LAUNCH_CHECK();

@@ -27,7 +27,7 @@ def genconv_aggregate_backward(ctx, grad_out):
     x, edge_attr = ctx.saved_tensors
     owner = ctx.owner
     t, p, y, msg_scale = ctx.scalars
-    prm, keep = _native.genconv_params(owner.aggr, t, p, y, getattr(owner, "eps", 1e-7), msg_scale,
+    prm, keep = _native.genconv_params(ctx.aggr, t, p, y, getattr(owner, "eps", 1e-7), msg_scale,
                                        add_residual=ctx.residual)
     prm.raw_message = int(ctx.raw)
     need = ctx.needs_input_grad

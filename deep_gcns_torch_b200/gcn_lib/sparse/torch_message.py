@@ -1,6 +1,7 @@
 """Generalised message passing - API of the reference's gcn_lib/sparse/torch_message.py
 without PyG / torch_scatter: the aggregation runs in the fused CSR kernel of libdgcn."""
 import collections
+import os
 import threading
 
 import torch
@@ -15,26 +16,45 @@ _POWER = ("power", "power_sum")
 
 # Non-persistent cache of destination-sorted graphs (derived tensors must
 # not show up in state_dict).  All layers of a model share one edge_index, so one
-# entry serves a whole forward; entries pin the tensor they were built from.
+# entry serves a whole forward; entries pin the tensor they were built from.  An entry
+# remembers the stream it was built on and the event that ends the build: a consumer on
+# another stream waits for that event (no host sync), so a CSR is never read before it exists.
 _csr_cache = collections.OrderedDict()
 _csr_lock = threading.Lock()
-_CSR_CACHE_SIZE = 8
+CSR_CACHE_SIZE = int(os.environ.get("DGCN_CSR_CACHE", "4"))      # graphs kept; 0 disables the cache
 
 
-def csr_of(edge_index, num_nodes):
-    """(rowptr, src, eid) int32 for edge_index (2,E): rows = targets (edge_index[1]),
-    stable within a row.  Built once per (tensor, version) by dgcn_csr_build."""
+def clear_csr_cache():
+    with _csr_lock:
+        _csr_cache.clear()
+
+
+def csr_of(edge_index, num_nodes, cache=True):
+    """(rowptr, src, eid, hubs) int32 for edge_index (2,E): rows = targets (edge_index[1]),
+    stable within a row.  Built once per (tensor, version) by dgcn_csr_build.  cache=False
+    for one-off graphs (GenMessagePassing.aggregate on explicit messages)."""
+    if not cache or CSR_CACHE_SIZE <= 0:
+        return _native.csr_build(edge_index, int(num_nodes))
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, str(edge_index.device),
            int(num_nodes))
+    cur = torch.cuda.current_stream(edge_index.device) if edge_index.is_cuda else None
     with _csr_lock:
         hit = _csr_cache.get(key)
         if hit is not None:
             _csr_cache.move_to_end(key)
-            return hit[1]
+            _, csr, stream_id, done = hit
+            if cur is not None and stream_id != cur.cuda_stream:
+                cur.wait_event(done)
+            return csr
     csr = _native.csr_build(edge_index, int(num_nodes))
+    done, stream_id = None, None
+    if cur is not None:
+        done = torch.cuda.Event()
+        done.record(cur)
+        stream_id = cur.cuda_stream
     with _csr_lock:
-        _csr_cache[key] = (edge_index, csr)
-        while len(_csr_cache) > _CSR_CACHE_SIZE:
+        _csr_cache[key] = (edge_index, csr, stream_id, done)
+        while len(_csr_cache) > CSR_CACHE_SIZE:
             _csr_cache.popitem(last=False)
     return csr
 
@@ -44,7 +64,8 @@ class _AggregateFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, owner, csr, raw, residual, x, edge_attr, t, p, y, msg_scale):
-        prm, keep = _native.genconv_params(owner.aggr, t, p, y, getattr(owner, "eps", 1e-7),
+        ctx.aggr = owner._check_aggr()                    # None -> 'add' (PyG default), like the reference
+        prm, keep = _native.genconv_params(ctx.aggr, t, p, y, getattr(owner, "eps", 1e-7),
                                            msg_scale, add_residual=residual)
         prm.raw_message = int(raw)
         out = _native.genconv_aggregate(x, x, csr, prm, edge_attr) if not raw else \
@@ -111,7 +132,7 @@ class GenMessagePassing(nn.Module):
         t, p, y = self._scalars()
         n = int(dim_size) if dim_size is not None else int(index.max()) + 1
         pos = torch.arange(index.numel(), device=index.device)
-        csr = csr_of(torch.stack((pos, index)), n)
+        csr = csr_of(torch.stack((pos, index)), n, cache=False)     # throw-away graph: do not evict real ones
         return _AggregateFn.apply(self, csr, True, False, inputs, None, t, p, y, None)
 
 

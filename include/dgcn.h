@@ -90,10 +90,16 @@ typedef struct dgcn_basic_conv {
  * (gcn_lib/dense/torch_edge.py:19-29, DenseDilated): rank l*dilation for
  * l < k, or - stochastic branch - the k ranks listed in cols_host (a HOST
  * array drawn by the caller from the CPU generator, torch_edge.py:22-24). */
+/* flags: DGCN_KNN_EXACT_FP32 ranks with the fp32 FMA kernels only (no tensor-core
+ * pre-filter); the result is the same list either way - the switch exists for A/B
+ * tests and measurements and is a property of the CALL, not of the process. */
+enum dgcn_knn_flags { DGCN_KNN_DEFAULT = 0, DGCN_KNN_EXACT_FP32 = 1 };
 typedef struct dgcn_dilation {
   int64_t k;
   int64_t dilation;
   const int32_t* cols_host; /* NULL or k entries, each in [0, k*dilation) */
+  int32_t flags;            /* dgcn_knn_flags */
+  int32_t reserved;         /* must be 0 */
 } dgcn_dilation;
 
 /* Dilated kNN graph of every cloud of a batch.
@@ -250,9 +256,6 @@ int dgcn_gather_rows(const float* x, int64_t C, const int32_t* rows, int64_t R, 
  * events, returns the summed duration and launch count for `tag` and resets it.
  * --------------------------------------------------------------------- */
 int dgcn_debug_kernel_timing(int32_t enable);
-/* A/B switch of the small-K selection: 1 = tcgen05 pre-filter + exact re-rank (default),
- * 0 = fp32 FMA kernel only, -1 = re-read env DGCN_KNN_PATH ("ffma" | "tc").  Returns the old value. */
-int dgcn_debug_set_knn_path(int32_t path);
 int dgcn_debug_kernel_timing_read(const char* tag, double* total_ms, int64_t* launches);
 
 #ifdef __cplusplus

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from deep_gcns_torch_b200 import _native
     assert ctypes.sizeof(_native.BasicConvC) == 96
-    assert ctypes.sizeof(_native.DilationC) == 24
+    assert ctypes.sizeof(_native.DilationC) == 32
     assert ctypes.sizeof(_native.GenconvParamsC) == 80
     assert ctypes.sizeof(_native.CsrHubsC) == 40
 
