@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 
 class ResGCN28(torch.nn.Module):
     def __init__(self, D, in_channels=9, n_classes=13, k=20, channels=64, n_blocks=28):
+        """examples/sem_seg_dense/architecture.py:7-56 restated (block='res', conv='edge', stochastic eps=0.2)."""
         super().__init__()
         self.n_blocks = n_blocks
         self.knn = D.DenseDilatedKnnGraph(k, 1, True, 0.2)
@@ -75,19 +76,58 @@ class MRGCN28(torch.nn.Module):
 
 
 class DeeperGCN(torch.nn.Module):
+    """examples/ogb/ogbn_arxiv/model.py:10-140 restated for block='res+', conv='gen' (same attribute names =
+    same state_dict keys: tests/test_models_gpu.py loads the reference model's golden state_dict into it)."""
+
     def __init__(self, S, layers=56, hidden=128, in_channels=128, tasks=40):
         super().__init__()
-        self.enc = torch.nn.Linear(in_channels, hidden)
         self.gcns = torch.nn.ModuleList(S.GENConv(hidden, hidden, aggr="softmax_sg", t=0.1, mlp_layers=1, norm="batch")
                                         for _ in range(layers))
         self.norms = torch.nn.ModuleList(S.norm_layer("batch", hidden) for _ in range(layers))
-        self.pred = torch.nn.Linear(hidden, tasks)
+        self.node_features_encoder = torch.nn.Linear(in_channels, hidden)
+        self.node_pred_linear = torch.nn.Linear(hidden, tasks)
+
+    @property
+    def enc(self):
+        return self.node_features_encoder
+
+    @property
+    def pred(self):
+        return self.node_pred_linear
 
     def forward(self, x, edge_index):
         h = self.gcns[0](self.enc(x), edge_index)
         for l in range(1, len(self.gcns)):
             h = self.gcns[l](F.relu(self.norms[l - 1](h)), edge_index) + h
         return torch.log_softmax(self.pred(F.relu(self.norms[-1](h))), dim=-1)
+
+    def forward_fused(self, x, edge_index):
+        """Same arithmetic with the opt-in fused 'res+' block (gcn_lib.sparse.fused): 2 launches per layer."""
+        from deep_gcns_torch_b200.gcn_lib.sparse.fused import res_plus_block
+        h = self.gcns[0](self.enc(x), edge_index)
+        for l in range(1, len(self.gcns)):
+            h = res_plus_block(self.gcns[l], self.norms[l - 1], h, edge_index)
+        return torch.log_softmax(self.pred(F.relu(self.norms[-1](h))), dim=-1)
+
+    def forward_partitioned(self, x_local, part, layers=None, overlap=True, head=True):
+        """Node-partitioned forward (deep_gcns_torch_b200.partition): every rank holds the rows
+        [part.lo, part.hi) of x and of the result; one halo all-to-all per layer, overlapped with the
+        interior rows; activations ping-pong between the partition's two persistent buffers."""
+        from deep_gcns_torch_b200 import partition as P
+        from deep_gcns_torch_b200.gcn_lib.sparse.fused import res_plus_block_partitioned
+        L = len(self.gcns) if layers is None else layers
+        C = self.enc.out_features
+        torch.addmm(self.enc.bias, x_local, self.enc.weight.t(), out=part.local_rows(C, 0))
+        a = P.aggregate_partitioned(self.gcns[0], part, C, slot=0, overlap=overlap)
+        lin = self.gcns[0].mlp[0]
+        h = torch.addmm(lin.bias, a, lin.weight.t(), out=part.local_rows(C, 1))
+        slot = 1
+        for l in range(1, L):
+            h = res_plus_block_partitioned(self.gcns[l], self.norms[l - 1], part, C, slot, scratch=a, overlap=overlap)
+            slot ^= 1
+        if not head:
+            return h
+        return torch.log_softmax(self.pred(F.relu(self.norms[L - 1](h))), dim=-1)
 
 
 def timeit(fn, steps=5):
@@ -153,7 +193,10 @@ def main():
         model = DeeperGCN(S).to(dev).eval()
         with torch.no_grad():
             ms = timeit(lambda: model(x, ei))
-        out["c3_deepergcn56"] = {"model_ms": ms, "edges_per_s": 56 * ei.shape[1] / (ms * 1e-3), "E": int(ei.shape[1])}
+            ms_fused = timeit(lambda: model.forward_fused(x, ei))
+            torch.testing.assert_close(model.forward_fused(x, ei), model(x, ei), rtol=1e-3, atol=1e-4)
+        out["c3_deepergcn56"] = {"model_ms": ms, "model_ms_fused_blocks": ms_fused,
+                                 "edges_per_s": 56 * ei.shape[1] / (ms_fused * 1e-3), "E": int(ei.shape[1])}
     print(json.dumps(out))
 
 

@@ -57,6 +57,11 @@ class GenconvParamsC(ctypes.Structure):
                 ("add_residual", c_i32), ("raw_message", c_i32)]
 
 
+class GenconvFusionC(ctypes.Structure):
+    _fields_ = [("pre_scale", c_f32p), ("pre_shift", c_f32p), ("pre_relu", c_i32), ("skip_hubs", c_i32),
+                ("row_list", ctypes.c_void_p), ("n_rows", c_i64)]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -95,6 +100,9 @@ def _declare(lib):
     lib.dgcn_genconv_aggregate.restype = ctypes.c_int
     lib.dgcn_genconv_aggregate.argtypes = [vp, vp, c_i64, c_i64, vp, vp, vp, vp, ctypes.POINTER(GenconvParamsC),
                                            ctypes.POINTER(CsrHubsC), vp, vp]
+    lib.dgcn_genconv_aggregate_fused.restype = ctypes.c_int
+    lib.dgcn_genconv_aggregate_fused.argtypes = [vp, vp, c_i64, c_i64, vp, vp, vp, vp, ctypes.POINTER(GenconvParamsC),
+                                                 ctypes.POINTER(CsrHubsC), ctypes.POINTER(GenconvFusionC), vp, vp]
     lib.dgcn_csr_hub_rows.restype = ctypes.c_int
     lib.dgcn_csr_hub_rows.argtypes = [vp, c_i64, c_i64, c_i32, c_i32, vp, vp, vp, vp]
     lib.dgcn_genconv_aggregate_backward.restype = ctypes.c_int
@@ -386,23 +394,45 @@ def genconv_params(aggr, t=1.0, p=1.0, y=0.0, eps=1e-7, msg_scale=None, add_resi
     return prm, keep
 
 
-def genconv_aggregate(x_src, x_dst, csr, prm, edge_attr=None):
-    """dgcn_genconv_aggregate: out (N, C) = x_dst + MsgNorm(aggregate(message))."""
+def genconv_aggregate(x_src, x_dst, csr, prm, edge_attr=None, out=None, pre=None, rows=None, skip_hubs=False):
+    """dgcn_genconv_aggregate(_fused): out (N, C) = x_dst + MsgNorm(aggregate(message)).
+
+    out: write into this (N, C) tensor (e.g. a view of a persistent buffer) instead of a new one.
+    pre = (scale (C), shift (C), relu): rows of x_src / x_dst are read as act(scale * x + shift).
+    rows (int32) / skip_hubs: destination rows of this launch (dgcn_genconv_fusion)."""
     rowptr, src, eid = csr[:3]
-    _require_cuda(x_src, x_dst, rowptr, src, eid, edge_attr)
+    _require_cuda(x_src, x_dst, rowptr, src, eid, edge_attr, out, rows)
     x_src, x_dst, edge_attr = _f32(x_src), _f32(x_dst), _f32(edge_attr)
     N, C = rowptr.numel() - 1, x_src.shape[1]
     dev = x_src.device
     hubs = None
     with torch.cuda.device(dev):
         if len(csr) > 3 and csr[3] is not None:
-            items, rows, counts, n_items = csr[3]
+            items, hrows, counts, n_items = csr[3]
             partial = torch.empty(n_items * 3 * C, dtype=torch.float32, device=dev)
-            hubs = CsrHubsC(_ptr(items), _ptr(rows), _ptr(counts), HUB_MIN_DEGREE, HUB_SEG_EDGES, _ptr(partial))
-        out = torch.empty((N, C), dtype=torch.float32, device=dev)
-        rc = lib().dgcn_genconv_aggregate(_ptr(x_src), _ptr(x_dst), N, C, _ptr(rowptr), _ptr(src), _ptr(eid),
-                                          _ptr(edge_attr), ctypes.byref(prm),
-                                          ctypes.byref(hubs) if hubs is not None else None, _ptr(out), _stream(dev))
+            hubs = CsrHubsC(_ptr(items), _ptr(hrows), _ptr(counts), HUB_MIN_DEGREE, HUB_SEG_EDGES, _ptr(partial))
+        if out is None:
+            out = torch.empty((N, C), dtype=torch.float32, device=dev)
+        elif out.shape != (N, C) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise RuntimeError("genconv_aggregate: out must be a contiguous fp32 (N, C) tensor")
+        fus, keep = None, None
+        if pre is not None or rows is not None or skip_hubs:
+            fus = GenconvFusionC()
+            if pre is not None:
+                keep = (_f32(pre[0]), _f32(pre[1]))
+                fus.pre_scale, fus.pre_shift, fus.pre_relu = _ptr(keep[0]), _ptr(keep[1]), int(bool(pre[2]))
+            fus.skip_hubs = int(bool(skip_hubs))
+            if rows is not None:
+                if rows.dtype != torch.int32 or not rows.is_contiguous():
+                    raise RuntimeError("genconv_aggregate: rows must be a contiguous int32 tensor")
+                fus.row_list, fus.n_rows = (rows.data_ptr() or None), rows.numel()
+                if rows.numel() == 0 and skip_hubs:
+                    return out
+        rc = lib().dgcn_genconv_aggregate_fused(_ptr(x_src), _ptr(x_dst), N, C, _ptr(rowptr), _ptr(src), _ptr(eid),
+                                                _ptr(edge_attr), ctypes.byref(prm),
+                                                ctypes.byref(hubs) if hubs is not None else None,
+                                                ctypes.byref(fus) if fus is not None else None, _ptr(out),
+                                                _stream(dev))
         _check(rc, "dgcn_genconv_aggregate")
     return out
 
@@ -429,13 +459,14 @@ def genconv_aggregate_backward(x_src, x_dst, csr, prm, grad_out, edge_attr=None,
     return gsrc, gdst, gea, gsc
 
 
-def gather_rows(x, rows):
-    _require_cuda(x, rows)
+def gather_rows(x, rows, out=None):
+    _require_cuda(x, rows, out)
     x = _f32(x)
     rows = rows.to(torch.int32).contiguous()
     R, C = rows.numel(), x.shape[1]
     with torch.cuda.device(x.device):
-        out = torch.empty((R, C), dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.empty((R, C), dtype=torch.float32, device=x.device)
         _check(lib().dgcn_gather_rows(_ptr(x), C, _ptr(rows), R, _ptr(out), _stream(x.device)), "dgcn_gather_rows")
     return out
 

@@ -148,10 +148,10 @@ constexpr uint32_t kIdescBf16MnMn128x128 =
     (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 // ---- operand split ----------------------------------------------------------------------------
-// planes (B, TC_PLANES, Cpad, N) bf16: x = hi + mid up to 2^-17 relative (|x - hi - mid| <= 2^-18 |x|);
+// planes (B, TC_PLANES, Cpad, N) bf16: x = hi + mid with |mid| <= 2^-8 |x| and |x - hi - mid| <= 2^-17 |x|;
 // channels >= C are zero.  Three bf16 products hi*hi, hi*mid, mid*hi reproduce x_i.x_j to
-// 3 * 2^-18 relative to |x_i||x_j| (two split residuals + the dropped mid*mid term) - a pre-filter
-// accuracy, the ranking itself is redone in exact fp32.
+// 2^-15 relative to |x_i||x_j| in the worst case (two split residuals 2^-16 + the dropped mid*mid
+// term 2^-16) - a pre-filter accuracy, the ranking itself is redone in exact fp32.
 constexpr int TC_PLANES = 2;
 
 // One pass over x for everything the tensor-core path needs: sq (B,N) (same FMA chain as sqnorm_kernel),
@@ -721,10 +721,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
     if (ok && cut < INFINITY) {
       const float dk = ordered_to_float(static_cast<uint32_t>(kth >> 32));
       const float smax = __ldg(t.sqmax + b);
-      // |approx - exact fp32| <= eps: 3 bf16 products of the (hi, mid) split (2 x 3 x 2^-18 < 2 x 2^-15.5 rel. to |x_i||x_j|),
-      // ~4*Cpad fp32 tensor-core accumulations and Cpad FMA-chain roundings (2^-23 each), the -|x_j|^2/2 term
-      // accumulated with them (3-term bf16 split, roundings at magnitude <= smax/2) and the final additions (2^-20).
-      const float eps = (2.0f * (2.158e-5f + (5.0f * Cpad + 8.0f) * 1.1921e-7f)) * sqrtf(sqq * smax) +
+      // |approx - exact fp32| <= eps.  Split error of x = hi + mid (bf16 round-to-nearest): |mid| <= 2^-8 |x|,
+      // |x - hi - mid| <= 2^-17 |x|, so the dropped mid*mid product is <= 2^-16 |x_i||x_j| and the two residual
+      // products together <= 2^-16 |x_i||x_j|: <= 2^-15 on x_i.x_j, 2 x 2^-15 = 2^-14 on the key.  Then ~4*Cpad
+      // fp32 tensor-core accumulations and Cpad FMA-chain roundings (2^-23 each), the -|x_j|^2/2 term accumulated
+      // with them (3-term bf16 split, roundings at magnitude <= smax/2) and the final additions (2^-20).
+      const float eps = (2.0f * (3.0518e-5f + (5.0f * Cpad + 8.0f) * 1.1921e-7f)) * sqrtf(sqq * smax) +
                         9.537e-7f * (sqq + smax);
       ok = (dk + eps < (PACKED ? cut : cut + sqq));
     }

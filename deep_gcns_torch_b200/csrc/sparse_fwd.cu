@@ -19,7 +19,11 @@ struct AggrArgs {
   // long rows (hubs): items = (row, segment) pairs, rows = (row, first item, #segments) triples
   const int32_t* hub_items; const int32_t* hub_item_count; const int32_t* hub_rows; const int32_t* hub_row_count;
   int hub_min_degree, hub_seg_edges; float* hub_partial;   // [item][3][C] merged (max, sum, weighted sum) states
+  // block fusion (dgcn_genconv_fusion): rows are read as act(pre_scale * x + pre_shift); MODE 0 walks row_list
+  const float* pre_scale; const float* pre_shift; int pre_relu;
+  const int32_t* row_list; int n_rows; int run_hubs;
 };
+
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -40,6 +44,17 @@ __device__ __forceinline__ VecF<VEC> load_vec(const float* p) {
     r.v[0] = __ldg(p);
   }
   return r;
+}
+
+// x -> act(s * x + t) on the VEC channels a lane owns (identity when no pre-activation is fused)
+template <int VEC>
+__device__ __forceinline__ void pre_apply(VecF<VEC>& v, const float (&s)[VEC], const float (&t)[VEC], bool on, bool relu) {
+  if (!on) return;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const float z = fmaf(s[j], v.v[j], t[j]);
+    v.v[j] = relu ? fmaxf(z, 0.f) : z;
+  }
 }
 
 // channel owned by (lane, block blk, slot j)
@@ -64,11 +79,14 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
   const int work_step = MODE == 2 ? static_cast<int>(gridDim.x * 8) : static_cast<int>(gridDim.x);
   for (int hub_it = work0; MODE != 0 ? hub_it < n_work : hub_it == work0; hub_it += work_step) {
   int row, seg = 0, item0 = 0, nseg = 0;
-  if (MODE == 0) row = static_cast<int>(blockIdx.x * (blockDim.x >> 5) + warp);
-  else if (MODE == 1) { row = __ldg(g.hub_items + 2 * hub_it); seg = __ldg(g.hub_items + 2 * hub_it + 1); }
+  if (MODE == 0) {
+    const int slot = static_cast<int>(blockIdx.x * (blockDim.x >> 5) + warp);
+    if (slot >= g.n_rows) return;
+    row = g.row_list ? __ldg(g.row_list + slot) : slot;
+  } else if (MODE == 1) { row = __ldg(g.hub_items + 2 * hub_it); seg = __ldg(g.hub_items + 2 * hub_it + 1); }
   else { row = __ldg(g.hub_rows + 3 * hub_it); item0 = __ldg(g.hub_rows + 3 * hub_it + 1); nseg = __ldg(g.hub_rows + 3 * hub_it + 2); }
-  if (MODE == 0 && row >= g.N) return;
   const int C = g.C;
+  const bool pre = g.pre_scale != nullptr;
   const int rbeg = __ldg(g.rowptr + row), rend = __ldg(g.rowptr + row + 1);
   const int deg = rend - rbeg;
   if (MODE == 0 && g.hub_rows != nullptr && deg >= g.hub_min_degree) return;   // the hub kernels own this row
@@ -86,9 +104,11 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
   for (int blk = 0; blk < NBLK; ++blk) {
     const int cbase = chan_of<VEC>(lane, blk, 0);
     const bool live = cbase < C;   // C % VEC == 0 so a lane's VEC channels are all in or all out
-    float M[VEC], S[VEC], W[VEC];
+    float M[VEC], S[VEC], W[VEC], ps[VEC], pt[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
+      ps[j] = (pre && live) ? __ldg(g.pre_scale + cbase + j) : 1.f;
+      pt[j] = (pre && live) ? __ldg(g.pre_shift + cbase + j) : 0.f;
       M[j] = -INFINITY;
       S[j] = 0.f;
       W[j] = (AGGR == DGCN_AGGR_MAX) ? -INFINITY : 0.f;
@@ -117,6 +137,7 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
             }
             if (have[u]) {
               xv[u] = load_vec<VEC>(g.x_src + static_cast<int64_t>(s) * C + cbase);
+              pre_apply<VEC>(xv[u], ps, pt, pre, g.pre_relu != 0);
               if (g.edge_attr) ev[u] = load_vec<VEC>(g.edge_attr + static_cast<int64_t>(ei) * C + cbase);
             }
           }
@@ -260,6 +281,15 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
     for (int j = 0; j < VEC; ++j) xr[blk][j] = 0.f;
     if (need_x && cbase < C) {
       VecF<VEC> xv = load_vec<VEC>(g.x_dst + static_cast<int64_t>(row) * C + cbase);
+      if (pre) {
+        float ps[VEC], pt[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          ps[j] = __ldg(g.pre_scale + cbase + j);
+          pt[j] = __ldg(g.pre_shift + cbase + j);
+        }
+        pre_apply<VEC>(xv, ps, pt, true, g.pre_relu != 0);
+      }
 #pragma unroll
       for (int j = 0; j < VEC; ++j) xr[blk][j] = xv.v[j];
     }
@@ -297,11 +327,11 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
 template <int VEC, int NBLK>
 static int launch_aggr(const AggrArgs& g, cudaStream_t stream) {
   const int warps = 8;
-  const unsigned grid = static_cast<unsigned>(ceil_div(g.N, warps));
+  const unsigned grid = static_cast<unsigned>(ceil_div(g.n_rows, warps));
 #define DGCN_AGGR_CASE(A)                                                                   \
   case A:                                                                                   \
-    genconv_aggregate_kernel<VEC, NBLK, A, 0><<<grid, warps * 32, 0, stream>>>(g);          \
-    if (g.hub_rows) {                                                                       \
+    if (grid) genconv_aggregate_kernel<VEC, NBLK, A, 0><<<grid, warps * 32, 0, stream>>>(g); \
+    if (g.hub_rows && g.run_hubs) {                                                                     \
       genconv_aggregate_kernel<VEC, NBLK, A, 1><<<592, 256, 0, stream>>>(g);                \
       genconv_aggregate_kernel<VEC, NBLK, A, 2><<<32, 256, 0, stream>>>(g);                 \
     }                                                                                       \
@@ -380,7 +410,16 @@ int dgcn_genconv_aggregate(const float* x_src, const float* x_dst, int64_t N, in
                            const int32_t* src, const int32_t* eid, const float* edge_attr,
                            const dgcn_genconv_params* prm, const dgcn_csr_hubs* hubs, float* out,
                            dgcn_stream_t stream) {
+  return dgcn_genconv_aggregate_fused(x_src, x_dst, N, C, rowptr, src, eid, edge_attr, prm, hubs, nullptr, out, stream);
+}
+
+int dgcn_genconv_aggregate_fused(const float* x_src, const float* x_dst, int64_t N, int64_t C, const int32_t* rowptr,
+                                 const int32_t* src, const int32_t* eid, const float* edge_attr,
+                                 const dgcn_genconv_params* prm, const dgcn_csr_hubs* hubs,
+                                 const dgcn_genconv_fusion* fus, float* out, dgcn_stream_t stream) {
   if (!x_src || !rowptr || !src || !prm || !out || N < 0 || C <= 0) return DGCN_ERR_BAD_ARG;
+  if (fus && ((fus->pre_scale == nullptr) != (fus->pre_shift == nullptr))) return DGCN_ERR_BAD_ARG;
+  if (fus && fus->row_list && (fus->n_rows < 0 || fus->n_rows > N)) return DGCN_ERR_BAD_ARG;
   if (!x_dst && (prm->msg_norm || prm->add_residual)) return DGCN_ERR_BAD_ARG;
   if (edge_attr && !eid) return DGCN_ERR_BAD_ARG;
   if (N == 0) return DGCN_OK;
@@ -394,6 +433,13 @@ int dgcn_genconv_aggregate(const float* x_src, const float* x_dst, int64_t N, in
   g.add_residual = prm->add_residual;
   g.raw = prm->raw_message;
   g.out = out;
+  g.n_rows = static_cast<int>(N);
+  g.run_hubs = 1;
+  if (fus) {
+    g.pre_scale = fus->pre_scale; g.pre_shift = fus->pre_shift; g.pre_relu = fus->pre_relu;
+    if (fus->row_list) { g.row_list = fus->row_list; g.n_rows = static_cast<int>(fus->n_rows); }
+    g.run_hubs = fus->skip_hubs ? 0 : 1;
+  }
   if (hubs && hubs->rows && hubs->items && hubs->counts && hubs->partial && hubs->min_degree > 0 &&
       hubs->seg_edges > 0) {
     g.hub_items = hubs->items; g.hub_item_count = hubs->counts; g.hub_rows = hubs->rows;

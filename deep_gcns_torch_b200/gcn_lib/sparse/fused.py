@@ -1,0 +1,87 @@
+"""Fused 'res+' block of DeeperGCN - opt-in, inference only.
+
+The reference writes the block as separate modules (examples/ogb/ogbn_arxiv/model.py:91-106):
+
+    h2 = norms[l-1](h); h2 = relu(h2); h2 = dropout(h2); h = gcns[l](h2, edge_index) + h
+
+In eval mode the BatchNorm1d is a per-channel affine, dropout is the identity and GENConv with
+mlp_layers=1 ends in one Linear.  `res_plus_block` runs the same arithmetic in two launches:
+
+    dgcn_genconv_aggregate_fused   reads h rows as relu(s*h + t) (gathered rows and the residual row),
+                                   message + aggregate + MsgNorm + (z_i + m_i)     -> a
+    cuBLAS GEMM (beta = 1)         h_out = h + a W^T, then + bias in place
+
+so the normalised / activated copy of h and the GENConv output before the skip connection are never
+written to HBM (three N x C passes fewer per layer).  A model opts in by replacing the four lines above
+with `h = res_plus_block(self.gcns[l], self.norms[l-1], h, edge_index)`; with autograd enabled, a
+training-mode norm or an unsupported layer shape the call falls back to the unfused module sequence.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ... import _native
+from .torch_message import csr_of
+
+__all__ = ["bn_eval_affine", "res_plus_block", "res_plus_block_partitioned", "fusable"]
+
+
+def bn_eval_affine(norm):
+    """(scale, shift) with norm(h) = scale * h + shift for an eval-mode BatchNorm1d (running statistics)."""
+    var, mean = norm.running_var, norm.running_mean
+    scale = torch.rsqrt(var + norm.eps)
+    if norm.weight is not None:
+        scale = scale * norm.weight
+    shift = -mean * scale
+    if norm.bias is not None:
+        shift = shift + norm.bias
+    return scale, shift
+
+
+def fusable(conv, norm, h):
+    """The fused kernels cover: no autograd, eval-mode BatchNorm1d with running statistics, GENConv whose MLP
+    is a single Linear (mlp_layers = 1) and no edge features."""
+    return (not torch.is_grad_enabled() and isinstance(norm, nn.BatchNorm1d) and not norm.training and
+            norm.running_var is not None and len(conv.mlp) == 1 and isinstance(conv.mlp[0], nn.Linear) and
+            not conv.encode_edge and h.is_cuda and h.dtype == torch.float32)
+
+
+def _prm(conv):
+    t, p, y = conv._scalars()
+    scale = conv.msg_norm.msg_scale if conv.msg_norm is not None else None
+    return _native.genconv_params(conv._check_aggr(), t, p, y, conv.eps, scale, add_residual=True)
+
+
+def _linear_plus(lin, a, h, out=None):
+    """h + a W^T + b with the skip connection riding on the GEMM's beta."""
+    res = torch.addmm(h, a, lin.weight.t(), out=out)
+    if lin.bias is not None:
+        res.add_(lin.bias)
+    return res
+
+
+def res_plus_block(conv, norm, h, edge_index, out=None, dropout=0.0):
+    """h <- GENConv(dropout(relu(norm(h))), edge_index) + h   (model.py:91-106), fused when `fusable`."""
+    if not fusable(conv, norm, h):
+        h2 = F.dropout(F.relu(norm(h)), p=dropout, training=conv.training)
+        return conv(h2, edge_index) + h
+    h = h.contiguous()
+    prm, _keep = _prm(conv)
+    scale, shift = bn_eval_affine(norm)
+    a = _native.genconv_aggregate(h, h, csr_of(edge_index, h.size(0)), prm, pre=(scale, shift, True))
+    return _linear_plus(conv.mlp[0], a, h, out=out)
+
+
+def res_plus_block_partitioned(conv, norm, part, channels, slot, scratch=None, group=None, overlap=True):
+    """The same block on a node partition (deep_gcns_torch_b200.partition): the layer input is the raw h in
+    part.local_rows(channels, slot); the halo exchange ships raw rows (the kernel applies norm -> relu on
+    read) and overlaps the interior rows; the result is written into the OTHER buffer slot, which is
+    returned, so a layer stack ping-pongs between the two persistent buffers without copies."""
+    from ... import partition as P
+    h = part.local_rows(channels, slot)
+    if not fusable(conv, norm, h):
+        raise RuntimeError("res_plus_block_partitioned: inference-only fused path (eval BatchNorm1d, mlp_layers=1)")
+    scale, shift = bn_eval_affine(norm)
+    a = P.aggregate_partitioned(conv, part, channels, slot=slot, pre=(scale, shift, True), out=scratch, group=group,
+                                overlap=overlap)
+    return _linear_plus(conv.mlp[0], a, h, out=part.local_rows(channels, slot ^ 1))

@@ -229,6 +229,30 @@ int dgcn_genconv_aggregate(const float* x_src, const float* x_dst, int64_t N, in
                            const dgcn_csr_hubs* hubs /* may be NULL */, float* out,
                            dgcn_stream_t stream);
 
+/* Block fusion around the aggregate (DeeperGCN 'res+' block,
+ * examples/ogb/ogbn_arxiv/model.py:91-106: h <- GENConv(relu(norm(h))) + h) and the split launch
+ * that lets a node-partitioned layer overlap its halo exchange:
+ *   pre_scale / pre_shift (C) or both NULL: every row read from x_src and x_dst is taken as
+ *     act(pre_scale * x + pre_shift) (eval-mode BatchNorm1d folded to an affine, act = relu when
+ *     pre_relu != 0), so the normalised / activated copy of h is never written to HBM;
+ *   row_list (n_rows int32) or NULL: destination rows this launch processes (NULL = all N rows):
+ *     interior rows (all sources local) first, boundary rows once the halo has arrived;
+ *   skip_hubs != 0: rows of degree >= hubs->min_degree are left to a later launch. */
+typedef struct dgcn_genconv_fusion {
+  const float* pre_scale;
+  const float* pre_shift;
+  int32_t pre_relu;
+  int32_t skip_hubs;
+  const int32_t* row_list;
+  int64_t n_rows;
+} dgcn_genconv_fusion;
+int dgcn_genconv_aggregate_fused(const float* x_src, const float* x_dst, int64_t N, int64_t C,
+                                 const int32_t* rowptr, const int32_t* src, const int32_t* eid,
+                                 const float* edge_attr, const dgcn_genconv_params* prm,
+                                 const dgcn_csr_hubs* hubs /* may be NULL */,
+                                 const dgcn_genconv_fusion* fus /* may be NULL */, float* out,
+                                 dgcn_stream_t stream);
+
 /* Gradient of dgcn_genconv_aggregate w.r.t. x (both roles), edge_attr and the
  * scalar parameters.  The softmax weights carry gradient only when
  * softmax_grad != 0 (reference: learn_t, torch_message.py:51-55).

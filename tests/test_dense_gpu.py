@@ -223,15 +223,57 @@ def test_headline_shape_properties():
     d = (xt[:, rows].unsqueeze(2) - xt.gather(1, nn_idx[:, rows].reshape(16, -1, 1).expand(-1, -1, 64))
          .view(16, rows.numel(), 20, 64)).pow(2).sum(-1)
     assert bool((d[..., 1:] - d[..., :-1] > -1e-3).all())
-    sub = x[:2]
-    ref = od.knn_matrix(sub, 20)
-    _adjudicate(sub, nn_idx[:2], ref[0])
+    # every one of the 16 clouds against the oracle (indices adjudicated, features on all rows whose
+    # neighbour SET agrees; the number of masked rows is bounded by the counted near-ties)
     p = od.params_from_module(mod.gconv.nn)
     p = {k: (v.cpu() if torch.is_tensor(v) else {kk: vv.cpu() for kk, vv in v.items()}) for k, v in p.items()}
-    ref_y = od.graph_conv(sub, ref, p, "edge", "relu", "batch")
-    same = (nn_idx[:2].cpu().sort(-1).values == ref[0].sort(-1).values).all(-1)
+    y_cpu, nn_cpu = y1.cpu(), nn_idx.cpu()
+    for b0 in range(0, 16, 4):
+        sub = x[b0:b0 + 4]
+        ref = od.knn_matrix(sub, 20)
+        n_bad = _adjudicate(sub, nn_cpu[b0:b0 + 4], ref[0], max_frac=5e-4)
+        ref_y = od.graph_conv(sub, ref, p, "edge", "relu", "batch")
+        same = (nn_cpu[b0:b0 + 4].sort(-1).values == ref[0].sort(-1).values).all(-1)
+        assert int((~same).sum()) <= n_bad                       # a row is masked only where a near-tie was counted
+        mask = same.unsqueeze(1).unsqueeze(-1).expand_as(ref_y)
+        torch.testing.assert_close(y_cpu[b0:b0 + 4][mask], ref_y[mask], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("k,d,conv", [(20, 5, "edge"), (20, 27, "edge"), (20, 8, "mr")])
+def test_large_k_at_full_cloud_size_vs_oracle(k, d, conv):
+    """K = k*d > 48 at N = 4096 (the 25 dilated layers of ResGCN-28, config 2): the large-K selection at the
+    size where its slab tiling, sampled bound / retry and exact-fallback list are actually exercised; one cloud
+    through the oracle (full sorted K list, dilated list, fused convolution)."""
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    g = torch.Generator().manual_seed(k * d)
+    torch.manual_seed(2)
+    x = torch.randn(2, 64, 4096, 1, generator=g)
+    mod = D.DynConv2d(64, 64, k, d, conv, "relu", "batch", True)
+    p = od.params_from_module(mod.gconv.nn)
+    mod = mod.cuda().eval()
+    xc = x.cuda()
+    with torch.no_grad():
+        full = D.dense_knn_matrix(xc, k * d)
+        ei = mod.dilated_knn_graph(xc)
+        y = mod(xc)
+    assert torch.equal(ei, full[:, :, :, ::d])
+    ref_full = od.knn_matrix(x[:1], k * d)
+    _adjudicate(x[:1], full[0][:1], ref_full[0], max_frac=1e-3)
+    ref_ei = ref_full[:, :, :, ::d]
+    ref_y = od.graph_conv(x[:1], ref_ei, p, conv, "relu", "batch")
+    same = (ei[0][:1].cpu().sort(-1).values == ref_ei[0].sort(-1).values).all(-1)
+    assert same.float().mean() > 0.99
     mask = same.unsqueeze(1).unsqueeze(-1).expand_as(ref_y)
-    torch.testing.assert_close(y1[:2].cpu()[mask], ref_y[mask], rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(y[:1].cpu()[mask], ref_y[mask], rtol=RTOL, atol=ATOL)
+    # second cloud: size-independent properties (self first, no duplicates, ascending fp64 distances on a sample)
+    nn2 = full[0][1]
+    assert torch.equal(nn2[:, 0], torch.arange(4096, device="cuda"))
+    srt = nn2.sort(-1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())
+    xt = xc[1].squeeze(-1).t().double()
+    rows = torch.arange(0, 4096, 173, device="cuda")
+    dd = (xt[rows].unsqueeze(1) - xt[nn2[rows]]).pow(2).sum(-1)
+    assert bool((dd[:, 1:] - dd[:, :-1] > -1e-3).all())
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 1024, 20, 1), (2, 3, 512, 20, 1), (1, 32, 256, 9, 3), (3, 9, 384, 9, 2),

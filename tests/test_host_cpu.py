@@ -39,6 +39,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_native.DilationC) == 32
     assert ctypes.sizeof(_native.GenconvParamsC) == 80
     assert ctypes.sizeof(_native.CsrHubsC) == 40
+    assert ctypes.sizeof(_native.GenconvFusionC) == 40
 
 
 def test_no_cpu_fallback():
@@ -149,8 +150,9 @@ def test_bench_line_carries_every_contract_key():
     class Args:
         steps, warmup = 20, 1
 
-    loc = dict(world=2, args=Args, ms=11.4, ms_e2e=12.7, clk={"sm_mhz": 1965.0}, achieved=66.0, peak=6563.9,
-               traffic=72000000, peak_src="measured", kernel_ms=0.507, tensor_peak=1691.8, fp32_peak=74.45, sm_max=1965.0)
+    loc = dict(world=2, args=Args, ms=11.4, ms_e2e=12.7, clk={"sm_mhz": 1965.0}, achieved=220.0, peak=6563.9,
+               traffic=72000000, peak_src="measured", kernel_ms=0.507, tensor_peak=1691.8, sm_max=1965.0,
+               hbm_achieved=66.0, tensor_flop=1.1e11, numa={"numa_node": 0})
     out = eval(compile(ast.Expression(lit), path, "eval"), g, loc)
     json.dumps(out)
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -158,6 +160,8 @@ def test_bench_line_carries_every_contract_key():
         assert key in out, key
     assert out["warmup"] >= 3 and out["n_gpus"] == 2 and out["scaling"] == "weak" and out["vs_baseline"] is None
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(out["roofline"])
+    assert out["roofline"]["bound"] in ("hbm", "tensor") and out["roofline"]["unit"] == "TFLOP/s"
+    assert abs(out["roofline"]["frac"] - 220.0 / 1691.8) < 1e-9 and out["roofline"]["hbm"]["unit"] == "GB/s"
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(out["e2e"])
     assert "workload" in out["config"] and "model" not in out["config"]
     edges = 16 * 4096 * 20

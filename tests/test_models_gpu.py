@@ -1,0 +1,126 @@
+"""Model-level parity (BASELINE configs 2, 3, 4 in small): the drop-in classes assembled like the reference's
+own models (bench_models.py restates examples/*/architecture.py / model.py with the same attribute names)
+load the state_dict of the REFERENCE model and must reproduce its output.  Goldens:
+tests/golden/gen_golden_models.py (reference model sources executed on the unmodified gcn_lib)."""
+import os
+import sys
+
+import pytest
+import torch
+
+import golden_util as gu
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-3, 1e-4
+
+
+def _load_strict(model, sd):
+    res = model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    return model.cuda().eval()
+
+
+def _frac_bad(got, ref):
+    return float(((got - ref).abs() > ATOL + RTOL * ref.abs()).float().mean())
+
+
+def test_resgcn_4_blocks_matches_reference_model():
+    """DenseDeepGCN (sem_seg_dense): kNN head on inputs[:, 0:3], EdgeConv head, 3 ResDynBlock2d with dilation
+    1..3 (stochastic dilation in eval = regular dilation + one host RNG draw per layer), fusion, prediction.
+    A single fp32 near-tie in any layer's graph changes that point's neighbour set and, through the later
+    graphs, a few points' outputs: at most 1 % of the (cloud, point) columns may differ beyond tolerance."""
+    from bench_models import ResGCN28
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    c = gu.load("model_resgcn4")
+    m = c.meta
+    model = _load_strict(ResGCN28(D, m["in_channels"], m["n_classes"], m["k"], m["n_filters"], m["n_blocks"]), c.sd)
+    with torch.no_grad():
+        torch.manual_seed(5)
+        y = model(c.ins["inputs"].cuda()).cpu()
+    assert y.shape == c.outs["y"].shape
+    bad_cols = ((y - c.outs["y"]).abs() > ATOL + RTOL * c.outs["y"].abs()).any(1)       # (B, N)
+    assert float(bad_cols.float().mean()) <= 0.01, float(bad_cols.float().mean())
+
+
+def test_mrgcn_4_blocks_matches_reference_model():
+    """DeepGCN (modelnet_cls): DilatedKnnGraph head (self excluded), MRConv head, 3 ResDynBlock2d('mr') with
+    dilation 1..3, fusion + max/avg pooling + prediction."""
+    from bench_models import MRGCN28
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    c = gu.load("model_mrgcn4")
+    m = c.meta
+    model = _load_strict(MRGCN28(D, m["in_channels"], m["n_classes"], m["k"], m["n_filters"], m["n_blocks"],
+                                 m["emb_dims"]), c.sd)
+    with torch.no_grad():
+        y = model(c.ins["inputs"].cuda()).cpu()
+    # global pooling spreads one near-tie flip over every logit: 5e-3 instead of the per-layer 1e-3
+    torch.testing.assert_close(y, c.outs["y"], rtol=5e-3, atol=5e-4)
+
+
+def test_deepergcn_8_layers_res_plus_matches_reference_model():
+    from bench_models import DeeperGCN
+    from deep_gcns_torch_b200.gcn_lib import sparse as S
+    c = gu.load("model_deepergcn8")
+    m = c.meta
+    model = _load_strict(DeeperGCN(S, m["num_layers"], m["hidden_channels"], m["in_channels"], m["num_tasks"]), c.sd)
+    x, ei = c.ins["x"].cuda(), c.ins["edge_index"].long().cuda()
+    with torch.no_grad():
+        y = model(x, ei)
+        y_fused = model.forward_fused(x, ei)
+    torch.testing.assert_close(y.cpu(), c.outs["y"], rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(y_fused.cpu(), c.outs["y"], rtol=RTOL, atol=ATOL)     # opt-in fused res+ blocks
+
+
+class _Coupling(torch.nn.Module):
+    """eff_gcn_modules/rev/memgcn.py:9-52 restated (test infrastructure): chunk channels into groups, every
+    group's GENConv sees non-contiguous channel slices of x and of the edge features."""
+
+    def __init__(self, fms, group):
+        super().__init__()
+        self.Fms, self.group = fms, group
+
+    def forward(self, x, edge_index, *args):
+        xs = torch.chunk(x, self.group, dim=-1)
+        chunks = list(zip(*[torch.chunk(a, self.group, dim=-1) for a in args]))
+        y_in = sum(xs[1:])
+        ys = []
+        for i in range(self.group):
+            y_in = xs[i] + self.Fms[i](y_in, edge_index, *chunks[i])
+            ys.append(y_in)
+        return torch.cat(ys, dim=-1)
+
+    def inverse(self, y, edge_index, *args):
+        ys = torch.chunk(y, self.group, dim=-1)
+        chunks = list(zip(*[torch.chunk(a, self.group, dim=-1) for a in args]))
+        xs = []
+        for i in range(self.group - 1, -1, -1):
+            y_in = ys[i - 1] if i != 0 else sum(xs)
+            xs.append(ys[i] - self.Fms[i](y_in, edge_index, *chunks[i]))
+        return torch.cat(xs[::-1], dim=-1)
+
+
+def test_genconv_under_group_additive_coupling():
+    """RevGNN: GENConv called on chunked (strided, non-contiguous) inputs and edge features, forward and
+    inverse; the reconstruction must also close on our own outputs."""
+    from deep_gcns_torch_b200.gcn_lib import sparse as S
+    c = gu.load("model_revgnn")
+    m = c.meta
+    cg = m["C"] // m["group"]
+    fms = torch.nn.ModuleList(S.GENConv(cg, cg, aggr=m["aggr"], t=m["t"], learn_t=m["learn_t"], msg_norm=m["msg_norm"],
+                                        learn_msg_scale=m["learn_msg_scale"], norm=m["norm"], mlp_layers=m["mlp_layers"])
+                              for _ in range(m["group"]))
+    model = _load_strict(_Coupling(fms, m["group"]), c.sd)
+    x, ei, ea = c.ins["x"].cuda(), c.ins["edge_index"].long().cuda(), c.ins["edge_attr"].cuda()
+    with torch.no_grad():
+        y = model(x, ei, ea)
+        back_gold = model.inverse(c.outs["y"].cuda(), ei, ea)
+        back_own = model.inverse(y, ei, ea)
+    torch.testing.assert_close(y.cpu(), c.outs["y"], rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(back_gold.cpu(), c.outs["x_back"], rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(back_own, x, rtol=RTOL, atol=1e-3)
+    # and through autograd (the reversible wrapper differentiates through the module)
+    model.train()
+    xg = x.clone().requires_grad_(True)
+    model(xg, ei, ea).square().sum().backward()
+    assert torch.isfinite(xg.grad).all() and float(xg.grad.abs().sum()) > 0

@@ -40,9 +40,87 @@ def _worker(rank, world, port, out):
                                  part.n_local, "softmax", 0.3)
     full = x + osp.aggregate(osp.message(x, ei), ei[1], N, "softmax", 0.3)
     torch.testing.assert_close(h, full[lo:hi], rtol=1e-6, atol=1e-6)
+    # persistent-buffer path: the layer input sits in the buffer's local region, the halo lands behind it
+    part.local_rows(C).copy_(x[lo:hi])
+    assert P.start_halo_exchange(part, C) is None                          # CPU: synchronous
+    xbuf, _send = part.buffers(C)
+    assert torch.equal(xbuf, x_src) and xbuf.data_ptr() == part.buffers(C)[0].data_ptr()
+    # interior rows never read a halo row, boundary rows do; together they cover the rank's rows
+    src_l, dst_l = part.local_edge_index
+    reads_halo = torch.zeros(part.n_local, dtype=torch.bool)
+    reads_halo[dst_l[src_l >= part.n_local]] = True
+    assert torch.equal(part.interior_rows.long(), (~reads_halo).nonzero()[:, 0])
+    assert torch.equal(part.boundary_rows.long(), reads_halo.nonzero()[:, 0])
+    assert part.halo_bytes(C) == part.n_halo * C * 4
+    # reverse exchange: d/dx of sum(w * [local | halo]) through HaloExchange equals the single-process gradient
+    w = torch.randn(N, C, generator=g)
+    xl = x[lo:hi].clone().requires_grad_(True)
+    xs = P.HaloExchange.apply(xl, part, None)
+    w_src = torch.cat((w[lo:hi], w[part.halo_nodes]))
+    (xs * w_src).sum().backward()
+    # every rank r' that needs my row i contributes w[i]; plus my own copy
+    need = torch.zeros(N)
+    for r in range(world):
+        pr = P.GraphPartition(ei, N, r, world, device=torch.device("cpu"))
+        need[pr.halo_nodes] += 1
+    expect = w[lo:hi] * (1 + need[lo:hi]).unsqueeze(1)
+    torch.testing.assert_close(xl.grad, expect, rtol=1e-6, atol=1e-6)
     out[rank] = (part.n_halo, sum(part.send_counts))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _world1_worker(rank, world, port, out):
+    """world = 1 and a block-diagonal graph: empty halo lists everywhere must be legal."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deep_gcns_torch_b200 import partition as P
+    g = torch.Generator().manual_seed(1)
+    N, C = 40, 6
+    lo, hi = P.row_ranges(N, world)[rank]
+    n = hi - lo
+    ei = torch.stack((torch.randint(lo, hi, (200,), generator=g), torch.randint(lo, hi, (200,), generator=g)))
+    part = P.GraphPartition.from_local_edges(ei[0], ei[1], N, rank, world).exchange_halo_lists()
+    assert part.n_halo == 0 and part.send_rows.numel() == 0 and part.boundary_rows.numel() == 0
+    x = torch.randn(n, C, generator=g)
+    assert torch.equal(P.halo_exchange(x, part), x)
+    part.local_rows(C).copy_(x)
+    P.start_halo_exchange(part, C)
+    assert torch.equal(part.buffers(C)[0], x)
+    out[rank] = True
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_empty_halo_world1_and_block_diagonal_world2():
+    for world in (1, 2):
+        mgr = mp.Manager()
+        out = mgr.dict()
+        mp.spawn(_world1_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert len(out) == world
+
+
+def test_bfs_order_recovers_locality():
+    """A banded graph whose ids were shuffled: the Cuthill-McKee order brings the halo of a contiguous
+    4-way split back from 'almost everything' to a few band widths."""
+    from deep_gcns_torch_b200 import partition as P
+    g = torch.Generator().manual_seed(0)
+    N, band, world = 4000, 6, 4
+    i = torch.arange(N).repeat_interleave(band)
+    j = (i + torch.randint(1, band + 1, (N * band,), generator=g)).clamp(max=N - 1)
+    ei = torch.cat((torch.stack((i, j)), torch.stack((j, i))), 1)
+    shuffle = torch.randperm(N, generator=g)
+    ei_shuffled = shuffle[ei]
+
+    def total_halo(e):
+        return sum(P.GraphPartition(e, N, r, world).n_halo for r in range(world))
+    order = P.bfs_order(ei_shuffled, N)
+    assert torch.equal(torch.sort(order).values, torch.arange(N))          # a permutation
+    ei_new, perm = P.relabel(ei_shuffled, order)
+    assert torch.equal(perm[order], torch.arange(N))
+    before, after, ideal = total_halo(ei_shuffled), total_halo(ei_new), total_halo(ei)
+    assert before > 0.5 * N * (world - 1) / world * world * 0.5            # shuffled: most remote nodes are halo
+    assert after <= 4 * max(ideal, 2 * band * (world - 1)), (before, after, ideal)
 
 
 def test_halo_exchange_world2_gloo():

@@ -194,3 +194,45 @@ def test_sparse_graph_builders_match_golden_and_oracle():
     assert (got.cpu() == c.outs["stochastic_k5_d3_seed11"].long()).float().mean() > 0.999
     with pytest.raises(NotImplementedError):
         S.DilatedKnnGraph(5, 1, knn="cluster")
+
+
+def test_partitioned_layer_emulated_on_one_gpu():
+    """The node-partitioned layer without NCCL: two partitions live on the one GPU, the halo all-to-all is
+    emulated by row copies, everything else is the product path - persistent [local | halo] buffers,
+    interior / boundary row lists (split launches), hub rows, fused pre-activation.  Must equal the
+    full-graph kernel bit for bit (same per-row edge order) and the oracle within tolerance."""
+    from deep_gcns_torch_b200 import _native, partition as P
+    from deep_gcns_torch_b200.gcn_lib import sparse as S
+    g = torch.Generator().manual_seed(3)
+    N, E, C, world = 5003, 90000, 128, 2
+    ei = torch.randint(0, N, (2, E), generator=g)
+    ei[1, :3000] = 11                                              # a hub row (>= 1024 edges) in partition 0
+    ei[0, 3000:9000] = torch.randint(0, N // 2, (6000,), generator=g)   # make partition 0 partly interior
+    ei[1, 3000:9000] = torch.randint(0, N // 4, (6000,), generator=g)
+    x = torch.randn(N, C, generator=g).cuda()
+    eic = ei.cuda()
+    s = (torch.rand(C, generator=g) + 0.5).cuda()
+    t = (torch.randn(C, generator=g) * 0.1).cuda()
+    parts = [P.GraphPartition(eic, N, r, world) for r in range(world)]
+    for aggr in ("softmax_sg", "power_sum", "mean"):
+        conv = S.GENConv(C, C, aggr=aggr, t=0.3, p=1.5, y=0.2, msg_norm=True, mlp_layers=1).cuda().eval()
+        tt, pp, yy = conv._scalars()
+        prm, _k = _native.genconv_params(conv._check_aggr(), tt, pp, yy, conv.eps, conv.msg_norm.msg_scale, True)
+        for pre in (None, (s, t, True)):
+            z = x if pre is None else torch.relu(x * s + t)
+            full = _native.genconv_aggregate(z, z, _native.csr_build(eic, N), prm)
+            ref = osp.genconv_pre_mlp(z.cpu(), ei, None, aggr, 0.3, 1.5, 0.2, float(conv.msg_norm.msg_scale), 1e-7)
+            for part in parts:
+                part.send_rows = torch.empty(0, dtype=torch.int32, device="cuda")     # no NCCL in this test
+                xbuf, _send = part.buffers(C)
+                xbuf[:part.n_local].copy_(x[part.lo:part.hi])
+                xbuf[part.n_local:].copy_(x[part.halo_nodes])                          # the emulated exchange
+                out = torch.full((part.n_local, C), float("nan"), device="cuda")
+                _native.genconv_aggregate(xbuf, xbuf[:part.n_local], part.csr(), prm, out=out, pre=pre,
+                                          rows=part.interior_rows, skip_hubs=True)
+                _native.genconv_aggregate(xbuf, xbuf[:part.n_local], part.csr(), prm, out=out, pre=pre,
+                                          rows=part.boundary_rows, skip_hubs=False)
+                assert part.interior_rows.numel() + part.boundary_rows.numel() == part.n_local
+                assert torch.equal(out, full[part.lo:part.hi]), (aggr, pre is not None, part.rank)
+            torch.testing.assert_close(full.cpu(), ref, rtol=RTOL, atol=ATOL)
+    assert parts[0].interior_rows.numel() > 0 and parts[0].boundary_rows.numel() > 0

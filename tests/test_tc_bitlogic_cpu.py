@@ -66,9 +66,18 @@ def test_three_product_bf16_split_error_is_inside_eps():
     """|approx - exact| of the pre-filter key against the certificate's eps: x = hi + mid in bf16, products
     hi*hi + hi*mid + mid*hi (mid*mid dropped), -|x_j|^2/2 as three bf16 terms, fp32 accumulation."""
     g = torch.Generator().manual_seed(0)
-    for C, scale in ((64, 1.0), (64, 30.0), (16, 0.01), (3, 5.0), (48, 1e3)):
+    for C, scale in ((64, 1.0), (64, 30.0), (16, 0.01), (3, 5.0), (48, 1e3), (16, -1.0), (64, -1.0)):
         cpad = (C + 15) // 16 * 16
-        x = torch.randn(512, C, generator=g) * scale
+        if scale < 0:
+            # adversarial for the split: every component sits at the worst case of both roundings
+            # (1 + 2^-8 + 2^-17: hi drops 2^-8, mid drops 2^-17), mixed with bf16-exact values and signs
+            worst = 1.0 + 2.0**-8 + 2.0**-17
+            pick = torch.randint(0, 3, (512, C), generator=g)
+            sign = torch.randint(0, 2, (512, C), generator=g) * 2.0 - 1.0
+            x = torch.where(pick == 0, torch.tensor(worst), torch.where(pick == 1, torch.tensor(1.5), torch.tensor(worst * 2)))
+            x = (x * sign).float()
+        else:
+            x = torch.randn(512, C, generator=g) * scale
         x[:8] = x[8:16] * (1 + 1e-4)                               # near-duplicates
         hi = x.to(torch.bfloat16).float()
         mid = (x - hi).to(torch.bfloat16).float()
@@ -87,7 +96,7 @@ def test_three_product_bf16_split_error_is_inside_eps():
         key = -2.0 * acc                                           # approximate |x_j|^2 - 2 x_i.x_j
         exact = (sq[None, :] - 2.0 * (x.double() @ x.double().t()))
         smax = sq.max()
-        eps = (2.0 * (2.158e-5 + (5.0 * cpad + 8.0) * 1.1921e-7)) * torch.sqrt(sq[:, None] * smax) \
+        eps = (2.0 * (3.0518e-5 + (5.0 * cpad + 8.0) * 1.1921e-7)) * torch.sqrt(sq[:, None] * smax) \
             + 9.537e-7 * (sq[:, None] + smax)
         err = (key.double() - exact).abs()
         # the kernel's exact side is an fp32 FMA chain: allow its own rounding (C * 2^-24 relative) on top
