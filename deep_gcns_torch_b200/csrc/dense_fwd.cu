@@ -52,6 +52,39 @@ static int next_pow2(int v) {
   return p;
 }
 
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda): resolved once, the pointer is a
+// write-once cache of a driver symbol.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static std::atomic<void*> cached{nullptr};
+  void* fn = cached.load(std::memory_order_acquire);
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    cached.store(fn, std::memory_order_release);
+  }
+  return reinterpret_cast<EncodeTiledFn>(fn);
+}
+// bf16 matrix (rows, cols) row-major -> tensor map with boxes of 64 columns (128 bytes) x box_rows rows, SWIZZLE_128B:
+// a box lands in shared memory as box_rows x 128 B rows with the 16-byte chunks XOR-swizzled by (row & 7), which is
+// the canonical MN-major UMMA layout of one 64-wide MN block.
+static int make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return DGCN_ERR_UNSUPPORTED;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  const cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? DGCN_OK : DGCN_ERR_CUDA;
+}
+
 // Tensor-core pre-filter path (knn_tc.cuh).  xt: node-major copy of x if the caller has one.
 static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const float* xt, int64_t* n_partial,
                          const ProloguePq* pqf) {
@@ -79,6 +112,11 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
   DGCN_LAUNCH_CHECK();
   if (!xt) xt = xt_own;
   TcArgs t{};
+  {
+    int rc = make_plane_map(&t.tm_planes, planes, static_cast<int64_t>(B) * TC_PLANES * cpad, N, cpad);
+    if (rc == DGCN_OK) rc = make_plane_map(&t.tm_sqp, sqp, static_cast<int64_t>(B) * 8, N, 8);
+    if (rc != DGCN_OK) return rc;
+  }
   t.a = a;
   t.planes = planes;
   t.sqp = sqp;

@@ -8,13 +8,17 @@
 //                     -|x_j|^2/2 into the product, the node-major fp32 copy, max |x|^2 (and the
 //                     EdgeConv node GEMM).
 //   knn_tc_kernel     one 128-thread CTA = 128 queries of a cloud, two CTAs per SM.  Query planes stay
-//                     resident in shared memory; candidate tiles of 128 points stream through one
-//                     cp.async stage in the canonical MN-major SWIZZLE_128B layout (x is
-//                     channel-major = MN-major, so no transposition anywhere).  The thread that
-//                     arrives last at the split barrier issues the tcgen05.mma chain (M=128, N=128,
-//                     K=16) of the NEXT tile into one of two TMEM accumulators while all 128 threads -
-//                     thread r owns TMEM lane r = query r - filter the other accumulator against
-//                     the thread's private threshold; survivors go to a private candidate buffer
+//                     resident in shared memory; candidate tiles of 128 points are brought in by TMA
+//                     (cp.async.bulk.tensor, 64-point x Cpad-channel boxes with SWIZZLE_128B = the
+//                     canonical MN-major UMMA layout: x is channel-major = MN-major, so no
+//                     transposition anywhere, and no thread spends instructions on the copy).  Thread 0
+//                     issues the TMA of tile t+1 as soon as the MMAs of tile t have released the stage
+//                     and, from a poll at the next 16-column boundary of its filter loop, the
+//                     tcgen05.mma chain (M=128, N=128, K=16) of tile t+1 into the other of two TMEM
+//                     accumulators - so load and MMA of the next tile run under the filter of the
+//                     current one.  All 128 threads - thread r owns TMEM lane r = query r - filter the
+//                     finished accumulator (tcgen05.ld of 16 columns in flight while the previous 16 are
+//                     tested) against the thread's private threshold; survivors go to a private candidate buffer
 //                     and from there into the query's register-resident sorted list of the KP best
 //                     APPROXIMATE keys (no atomics, no CTA barriers in the filter).
 //                     Afterwards each thread re-evaluates its KP candidates with the exact fp32
@@ -25,6 +29,7 @@
 //   knn_exact_rows_kernel  completes the (rare) uncertified queries with the exact fp32 brute
 //                     force, one CTA per query.
 #pragma once
+#include <cuda.h>          // CUtensorMap (type only: the encoder comes from cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include "knn.cuh"
 
@@ -72,6 +77,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (done) return;
     if (spin > (1u << 26)) __trap();
   }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// TMA: one 2-D box of the tensor behind `map` (coordinates innermost first) -> shared memory, completion
+// counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
 }
 __device__ __forceinline__ void cp_async16_addr(uint32_t smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
@@ -126,6 +159,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 lanes x 16 consecutive fp32 columns, NOT waited for: the registers are valid only after tmem_wait16 on them
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// tcgen05.wait::ld; the registers are in/out operands so that no use (or copy) of them is scheduled above the wait
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 
 // Shared-memory matrix descriptor, MN-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
@@ -317,6 +369,8 @@ __device__ __forceinline__ void ldg256(const float* p, float (&w)[8]) {
 }
 
 struct TcArgs {
+  CUtensorMap tm_planes;         // bf16 (B*2*Cpad rows, N) row-major, box 64 points x Cpad rows, SWIZZLE_128B
+  CUtensorMap tm_sqp;            // bf16 (B*8 rows, N), box 64 points x 8 rows, SWIZZLE_128B
   KnnArgs a;
   const __nv_bfloat16* planes;   // (B,2,Cpad,N)
   const __nv_bfloat16* sqp;      // (B,8,N): rows 0..2 = bf16 split of -|x|^2/2, rest zero
@@ -351,9 +405,10 @@ constexpr int TC_ISSUE_CHUNK = 2;                                 // 32-column c
 struct TcTail {
   uint64_t cbuf[TC_BUF * TC_THREADS];               // 16 KB private candidate buffers, slot-major
   uint64_t mbar;                                    // MMA of a tile has completed (tcgen05.commit)
-  uint64_t mbar_ready;                              // all 128 threads: next tile's operands landed, other accumulator drained
+  uint64_t mbar_drained;                            // all 128 threads have finished reading the accumulator the next MMA overwrites
+  uint64_t mbar_tma;                                // the next tile's operands have landed (TMA complete_tx)
+  uint64_t mbar_q;                                  // query planes + tile 0 have landed
   uint32_t tmem_base;
-  int issue_ticket;                                 // next tile whose MMAs have not been issued yet
   unsigned char ok[TILE];
 };
 
@@ -367,24 +422,6 @@ __host__ __device__ inline size_t tc_work_bytes(int KP, int k, bool wide, int nc
   const size_t stream = 2 * static_cast<size_t>(TC_STAGE_BYTES) + 2 * TC_XBLOCK_BYTES;
   const size_t w = after > stream ? after : stream;
   return (w + 1023) & ~static_cast<size_t>(1023);
-}
-
-// 128 threads copy one 128-point tile of the planes into `dst`.
-// Thread r always moves 16-byte chunk (r & 15) of rows (r >> 4) + 8n: the swizzle term and all
-// offsets except the row / plane strides are loop invariant.
-__device__ __forceinline__ void tc_load_tile(unsigned char* dst, const __nv_bfloat16* planes_b, int Cpad, int N,
-                                             int p0, int r) {
-  const int ch = r & 15, row0 = r >> 4;            // row0 in [0,8): (row & 7) == row0 for every row handled
-  const int blk = ch >> 3, c16 = ch & 7;
-  const int64_t plane = static_cast<int64_t>(Cpad) * N;
-  const __nv_bfloat16* src = planes_b + static_cast<int64_t>(row0) * N + p0 + ch * 8;
-  unsigned char* d = dst + blk * (Cpad * 128) + row0 * 128 + ((c16 ^ row0) << 4);
-  const int groups = Cpad >> 3;
-  for (int pl = 0; pl < TC_PLANES; ++pl) {
-    const __nv_bfloat16* sp = src + pl * plane;
-    unsigned char* dp = d + pl * (2 * Cpad * 128);
-    for (int n = 0; n < groups; ++n) cp_async16(dp + n * 1024, sp + static_cast<int64_t>(n) * 8 * N);
-  }
 }
 
 // Branch-free insertion of (nk, nv) into the ascending register-resident list (k, v):
@@ -415,7 +452,7 @@ __device__ __forceinline__ void reg_insert_packed(uint32_t (&k)[KP], uint32_t nk
 }
 
 template <int KP, bool PACKED>
-__global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
+__global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const __grid_constant__ TcArgs t) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // SWIZZLE_128B atoms must sit on 1024-byte boundaries of the shared address space
   unsigned char* work = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -426,42 +463,59 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
   const int b = blockIdx.y, q0 = blockIdx.x * TILE;
   const int N = a.N, Cpad = t.Cpad;
   const int plane_bytes = 2 * Cpad * 128;
-  const __nv_bfloat16* planes_b = t.planes + static_cast<int64_t>(b) * TC_PLANES * Cpad * N;
   const float* sqb = a.sq + static_cast<int64_t>(b) * N;
   unsigned char* qstage = work;
   unsigned char* stage = work + TC_STAGE_BYTES;
 
   if (tid == 0) {
     mbar_init(&sm.mbar, 1);
-    mbar_init(&sm.mbar_ready, TC_THREADS);
-    sm.issue_ticket = 1;
+    mbar_init(&sm.mbar_drained, TC_THREADS);
+    mbar_init(&sm.mbar_tma, 1);
+    mbar_init(&sm.mbar_q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(&sm.tmem_base, 256);     // two 128-column accumulators
   const int ntiles = N / TILE;
   unsigned char* qx = work + 2 * TC_STAGE_BYTES;          // query-side extra block: ones in K rows 0..2
   unsigned char* sx = qx + TC_XBLOCK_BYTES;               // candidate-side extra block: -|x_j|^2/2 split in rows 0..2
-  const __nv_bfloat16* sqp_b = t.sqp + static_cast<int64_t>(b) * 8 * N;
   for (int ch = tid; ch < TC_XBLOCK_BYTES / 16; ch += TC_THREADS) {   // whole rows are constant: no swizzle needed
     const int row = (ch >> 3) & 15;
     const uint32_t one2 = row < 3 ? 0x3F803F80u : 0u;
     reinterpret_cast<uint4*>(qx)[ch] = make_uint4(one2, one2, one2, one2);
-    reinterpret_cast<uint4*>(sx)[ch] = make_uint4(0u, 0u, 0u, 0u);        // rows 8..15 stay zero
+    reinterpret_cast<uint4*>(sx)[ch] = make_uint4(0u, 0u, 0u, 0u);        // rows 8..15 stay zero, TMA refreshes rows 0..7
   }
-  __syncthreads();                                        // the zero fill precedes the cp.async writes of rows 0..7
-  // candidate extra block: thread r moves 16-byte chunk (r & 15) of K row (r >> 4) (rows 0..7)
-  const uint32_t sx_dst = smem_u32(sx) + ((r & 15) >> 3) * 2048 + (r >> 4) * 128 + ((((r & 15) & 7) ^ (r >> 4)) << 4);
-  const __nv_bfloat16* sx_src = sqp_b + static_cast<int64_t>(r >> 4) * N + (r & 15) * 8;
-  tc_load_tile(qstage, planes_b, Cpad, N, q0, r);
-  tc_load_tile(stage, planes_b, Cpad, N, 0, r);
-  cp_async16_addr(sx_dst, sx_src);
-  cp_async_commit();
+  fence_proxy_async();                                    // generic-proxy fills above -> visible to TMA / tcgen05.mma
+  __syncthreads();                                        // barriers initialised, fills done
+  // One elected thread moves operands.  A tile = 2 planes x 2 MN blocks (boxes of 64 points x Cpad channels) plus
+  // the 2 x (64 points x 8 rows) boxes of the -|x_j|^2/2 block.
+  const uint32_t tile_bytes = static_cast<uint32_t>(2 * plane_bytes + 2 * 8 * 128);
+  auto tma_planes = [&](unsigned char* dst, int p0, uint64_t* bar) {
+#pragma unroll
+    for (int pl = 0; pl < TC_PLANES; ++pl)
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk)
+        tma_load_2d(smem_u32(dst) + pl * plane_bytes + blk * (Cpad * 128), &t.tm_planes, p0 + blk * 64,
+                    (b * TC_PLANES + pl) * Cpad, bar);
+  };
+  auto tma_sx = [&](int p0, uint64_t* bar) {
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) tma_load_2d(smem_u32(sx) + blk * 2048, &t.tm_sqp, p0 + blk * 64, b * 8, bar);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(&sm.mbar_q, static_cast<uint32_t>(2 * plane_bytes) + tile_bytes);
+    tma_planes(qstage, q0, &sm.mbar_q);
+    tma_planes(stage, 0, &sm.mbar_q);
+    tma_sx(0, &sm.mbar_q);
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(&sm.tmem_base, 256);     // two 128-column accumulators
+  }
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
   // One thread issues the 3 x Cpad/16 + 1 MMAs of a candidate tile into accumulator `buf` and commits.
   auto issue_tile = [&](uint32_t tmem_acc) {
     tc_fence_after();
     const uint32_t abase = smem_u32(qstage), bbase = smem_u32(stage);
-    const int pa[3] = {0, 0, 1};   // hi*hi, hi*mid, mid*hi  (mid*mid ~ 2^-18 |x_i||x_j| is inside eps)
+    const int pa[3] = {0, 0, 1};   // hi*hi, hi*mid, mid*hi  (mid*mid <= 2^-16 |x_i||x_j| is inside eps)
     const int pb[3] = {0, 1, 0};
     uint32_t acc = 0;
     for (int kk = 0; kk < Cpad / 16; ++kk) {
@@ -478,13 +532,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
               kIdescBf16MnMn128x128, 1u);
     umma_commit(&sm.mbar);
   };
-  cp_async_wait_all();
-  fence_proxy_async();
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();                                        // TMEM base address published
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  if (tid == 0) issue_tile(tmem);
+  if (tid == 0) {
+    mbar_wait(&sm.mbar_q, 0u);
+    issue_tile(tmem);
+  }
 
   const int qg = q0 + r;
   // the KP best approximate keys, ascending, in registers
@@ -555,19 +610,24 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
     thr_acc = -0.5f * tau_f;                        // the filter compares accumulators: key <= tau  <=>  acc >= -tau/2
   };
 
-  // Pipeline per tile t: wait MMA(t) -> the stage is free: cp.async tile t+1 -> filter first half of
-  // accumulator t&1 -> (loads landed) split barrier, issue MMA(t+1) into the other accumulator -> filter
-  // second half.  The split barrier also orders: every thread finished reading accumulator (t+1)&1
-  // (tile t-1) before it is overwritten.
+  // Pipeline per tile t: wait MMA(t) -> everybody: "my reads of the other accumulator are done" (mbar_drained);
+  // thread 0: TMA of tile t+1 into the stage MMA(t) has just released -> filter accumulator t&1 in 16-column
+  // chunks (the tcgen05.ld of the next chunk in flight); at every chunk boundary thread 0 polls {TMA landed, all
+  // drained} and then issues MMA(t+1) into the other accumulator - nobody waits for it before the next tile.
   for (int tile = 0; tile < ntiles; ++tile) {
     const int par = tile & 1;
     const bool more = tile + 1 < ntiles;
     mbar_wait(&sm.mbar, static_cast<uint32_t>(par));
     tc_fence_after();
+    bool to_issue = more && tid == 0;
     if (more) {
-      tc_load_tile(stage, planes_b, Cpad, N, (tile + 1) * TILE, r);
-      cp_async16_addr(sx_dst, sx_src + (tile + 1) * TILE);
-      cp_async_commit();
+      tc_fence_before();                 // my tcgen05.ld of accumulator par^1 (tile-1) are complete and ordered
+      mbar_arrive(&sm.mbar_drained);
+      if (tid == 0) {
+        mbar_expect_tx(&sm.mbar_tma, tile_bytes);
+        tma_planes(stage, (tile + 1) * TILE, &sm.mbar_tma);
+        tma_sx((tile + 1) * TILE, &sm.mbar_tma);
+      }
     }
     // filter: thread = TMEM lane = query; the accumulator is -key/2 with key = |x_j|^2 - 2 x_i.x_j
     // (row-constant |x_i|^2 omitted): admit when acc >= -tau/2
@@ -576,37 +636,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
     const uint32_t tacc = tmem + static_cast<uint32_t>(par * TILE) + lane_base;
     const uint32_t flush_bytes = PACKED ? (tile < 2 ? t.flush_early : t.flush_late) * TC_THREADS * 4u
                                         : TC_FLUSH_AT * TC_THREADS * 8u;
-#pragma unroll 1
-    for (int cchunk = 0; cchunk < TILE / 32; ++cchunk) {
-      if (cchunk == TC_ISSUE_CHUNK && more) {
-        // split barrier: everybody arrives (own loads landed and fenced, own reads of the other
-        // accumulator retired)
-        cp_async_wait_all();
-        fence_proxy_async();
-        tc_fence_before();
-        // whoever arrives last sees the phase complete and issues (the ticket settles races): nobody waits
-        if (mbar_arrive_completes(&sm.mbar_ready)) {
-          if (atomicCAS(&sm.issue_ticket, tile + 1, tile + 2) == tile + 1)
-            issue_tile(tmem + static_cast<uint32_t>((par ^ 1) * TILE));
-        }
-      }
-      float v[32];
-      __syncwarp();   // tcgen05.ld is warp-collective
-      tmem_ld32(tacc + static_cast<uint32_t>(cchunk * 32), v);
-      if (diag && (r >> 5) == cchunk) {   // self exclusion: only in the diagonal tile, only one column
+    // one 16-column chunk: test, buffer, flush when a lane's buffer runs full
+    auto filter16 = [&](uint32_t (&v)[16], int c16) {
+      if (diag && (r >> 4) == c16) {     // self exclusion: only in the diagonal tile, only one column
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i == (r & 31)) v[i] = -INFINITY;   // accumulator -inf = key +inf
+        for (int i = 0; i < 16; ++i)
+          if (i == (r & 15)) v[i] = 0xFF800000u;   // accumulator -inf = key +inf
       }
-      // PACKED: one LOP3 builds the entry (key & R & I) | (R ^ I) with R = ~0xFFF | index bits 5..11
-      // (tile, chunk) and the immediate I = ~0xFFF | index bits 0..4
-      const uint32_t rbits = 0xFFFFF000u | static_cast<uint32_t>(j0 + cchunk * 32);
+      // PACKED: one LOP3 builds the entry (key & R & I) | (R ^ I) with R = ~0xFFF | index bits 4..11
+      // (tile, chunk) and the immediate I = ~0xFFF | index bits 0..3
+      const uint32_t rbits = 0xFFFFF000u | static_cast<uint32_t>(j0 + c16 * 16);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint32_t jcur = static_cast<uint32_t>(j0 + cchunk * 32 + g * 8);
+      for (int g = 0; g < 2; ++g) {
+        uint32_t jcur = static_cast<uint32_t>(j0 + c16 * 16 + g * 8);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float acc = v[g * 8 + i];
+          const uint32_t accb = v[g * 8 + i];
           // if (!(acc < thr_acc)) { buffer[slot] = entry; ++slot; }  - predicated, no branch
           if (PACKED) {
             const uint32_t ibits = 0xFFFFF000u | static_cast<uint32_t>(g * 8 + i);
@@ -615,12 +660,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
                 ".reg .pred p;\n"
                 ".reg .b32 en;\n"
                 "lop3.b32 en, %1, %2, %5, 0xE6;\n"          // (a & b & c) | (b ^ c)
-                "setp.geu.f32 p, %1, %3;\n"
+                "setp.geu.f32 p, %6, %3;\n"
                 "@p st.shared.b32 [%0], en;\n"
                 "@p add.u32 %0, %0, %4;\n"
                 "}"
                 : "+r"(cb_addr)
-                : "r"(__float_as_uint(acc)), "r"(rbits), "f"(thr_acc), "n"(TC_THREADS * 4), "r"(ibits));
+                : "r"(accb), "r"(rbits), "f"(thr_acc), "n"(TC_THREADS * 4), "r"(ibits), "f"(__uint_as_float(accb)));
           } else {
             asm volatile(
                 "{\n"
@@ -630,12 +675,40 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const TcArgs t) {
                 "@p add.u32 %0, %0, %4;\n"
                 "}"
                 : "+r"(cb_addr)
-                : "f"(acc), "r"(jcur), "f"(thr_acc), "n"(TC_THREADS * 8));
+                : "f"(__uint_as_float(accb)), "r"(jcur), "f"(thr_acc), "n"(TC_THREADS * 8));
             ++jcur;
           }
         }
         if (__any_sync(0xffffffffu, cb_addr - cb_addr0 >= flush_bytes)) flush();
       }
+    };
+    auto poll_issue = [&]() {
+      if (to_issue && mbar_test(&sm.mbar_tma, static_cast<uint32_t>(par)) &&
+          mbar_test(&sm.mbar_drained, static_cast<uint32_t>(par))) {
+        issue_tile(tmem + static_cast<uint32_t>((par ^ 1) * TILE));
+        to_issue = false;
+      }
+    };
+    uint32_t va[16], vb[16];
+    __syncwarp();   // tcgen05.ld is warp-collective
+    tmem_ld16_async(tacc, va);
+#pragma unroll 1
+    for (int c16 = 0; c16 < TILE / 16; c16 += 2) {
+      poll_issue();
+      __syncwarp();
+      tmem_wait16(va);
+      tmem_ld16_async(tacc + static_cast<uint32_t>((c16 + 1) * 16), vb);
+      filter16(va, c16);
+      poll_issue();
+      __syncwarp();
+      tmem_wait16(vb);
+      if (c16 + 2 < TILE / 16) tmem_ld16_async(tacc + static_cast<uint32_t>((c16 + 2) * 16), va);
+      filter16(vb, c16 + 1);
+    }
+    if (to_issue) {   // (thread 0 only) the filter outran the loads: wait, then issue
+      mbar_wait(&sm.mbar_tma, static_cast<uint32_t>(par));
+      mbar_wait(&sm.mbar_drained, static_cast<uint32_t>(par));
+      issue_tile(tmem + static_cast<uint32_t>((par ^ 1) * TILE));
     }
   }
   flush();

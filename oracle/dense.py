@@ -35,7 +35,7 @@ def knn_matrix(x, K, dtype=None):
             xt = xt.to(dtype)
         B, N, _ = xt.shape
         _, nn_idx = torch.topk(-pairwise_distance(xt.detach()), k=K)
-        center = torch.arange(0, N).expand(B, K, -1).transpose(2, 1)
+        center = torch.arange(0, N, device=xt.device).expand(B, K, -1).transpose(2, 1)
     return torch.stack((nn_idx, center), dim=0)
 
 
@@ -52,7 +52,7 @@ def knn_exclude_self(x, K):
         d = (xt.unsqueeze(2) - xt.unsqueeze(1)).pow(2).sum(-1)
         d.diagonal(dim1=1, dim2=2).fill_(float("inf"))
         nn_idx = d.topk(K, dim=-1, largest=False).indices
-        center = torch.arange(0, N).view(1, N, 1).expand(B, N, K)
+        center = torch.arange(0, N, device=xt.device).view(1, N, 1).expand(B, N, K)
     return torch.stack((nn_idx, center), dim=0)
 
 
@@ -81,7 +81,7 @@ def batched_index_select(x, idx):
     """gcn_lib/dense/torch_nn.py:75-96.  x (B,C,N,1), idx (B,N,k) -> (B,C,N,k)."""
     B, C, N = x.shape[:3]
     k = idx.shape[-1]
-    flat = (idx + torch.arange(0, B).view(-1, 1, 1) * N).contiguous().view(-1)
+    flat = (idx + torch.arange(0, B, device=idx.device).view(-1, 1, 1) * N).contiguous().view(-1)
     rows = x.transpose(2, 1).contiguous().view(B * N, -1)[flat, :]
     return rows.view(B, N, k, C).permute(0, 3, 1, 2).contiguous()
 

@@ -43,6 +43,18 @@ def exec_reference(rel, name):
     return ns
 
 
+def capture(model):
+    """Forward hooks on the head / backbone blocks (features) and on every graph builder (neighbour lists)."""
+    feats, graphs, handles = [], [], []
+    handles.append(model.head.register_forward_hook(lambda m, i, o: feats.append(o.detach().clone())))
+    handles.append(model.knn.register_forward_hook(lambda m, i, o: graphs.append(o[0].to(torch.int32).clone())))
+    for blk in model.backbone:
+        handles.append(blk.register_forward_hook(lambda m, i, o: feats.append(o.detach().clone())))
+        handles.append(blk.body.dilated_knn_graph.register_forward_hook(
+            lambda m, i, o: graphs.append(o[0].to(torch.int32).clone())))
+    return feats, graphs, handles
+
+
 def main():
     torch.set_num_threads(8)
     ref_shims.load_reference()
@@ -57,10 +69,16 @@ def main():
     randomize_norm(model, gen)
     pos, feat = torch.rand(2, 256, 3, generator=gen), torch.rand(2, 256, 6, generator=gen)
     inputs = torch.cat((pos, feat), 2).transpose(1, 2).unsqueeze(-1).contiguous()
+    feats, graphs, handles = capture(model)
     with torch.no_grad():
         torch.manual_seed(5)                      # stochastic dilation draws torch.rand(1) per layer even in eval
         y = model(inputs)
-    save("model_resgcn4", dict(opt, B=2, N=256), {"inputs": inputs}, model.state_dict(), {"y": y})
+    for h in handles:
+        h.remove()
+    outs = {"y": y}
+    for i, (f, gph) in enumerate(zip(feats, graphs)):
+        outs["feat%d" % i], outs["graph%d" % i] = f, gph
+    save("model_resgcn4", dict(opt, B=2, N=256), {"inputs": inputs}, model.state_dict(), outs)
 
     # ---- config 4 in small: examples/modelnet_cls/architecture.py:11-81 -----------------------------------------
     ns = exec_reference("examples/modelnet_cls/architecture.py", "ref_modelnet")
@@ -70,9 +88,15 @@ def main():
     model = ns["DeepGCN"](types.SimpleNamespace(**opt)).eval()
     randomize_norm(model, gen)
     inputs = torch.rand(3, 3, 160, 1, generator=gen)
+    feats, graphs, handles = capture(model)
     with torch.no_grad():
         y = model(inputs)
-    save("model_mrgcn4", dict(opt, B=3, N=160), {"inputs": inputs}, model.state_dict(), {"y": y})
+    for h in handles:
+        h.remove()
+    outs = {"y": y}
+    for i, (f, gph) in enumerate(zip(feats, graphs)):
+        outs["feat%d" % i], outs["graph%d" % i] = f, gph
+    save("model_mrgcn4", dict(opt, B=3, N=160), {"inputs": inputs}, model.state_dict(), outs)
 
     # ---- config 3 in small: examples/ogb/ogbn_arxiv/model.py:10-140 ------------------------------------------------
     ns = exec_reference("examples/ogb/ogbn_arxiv/model.py", "ref_arxiv")

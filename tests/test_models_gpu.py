@@ -25,37 +25,76 @@ def _frac_bad(got, ref):
     return float(((got - ref).abs() > ATOL + RTOL * ref.abs()).float().mean())
 
 
+def _blockwise(model, c, tail):
+    """Every stage of the model on the REFERENCE's own stage input (no error accumulation): graph adjudicated
+    as a set per (cloud, point) row, features compared on the rows whose neighbour set agrees (a row differs
+    only at an fp32 near-tie, tests/test_dense_gpu.py adjudicates those against fp64); then the tail (fusion /
+    pooling / prediction, plain torch modules) on the reference's features; then the end-to-end output, where
+    one near-tie flip anywhere reaches every logit through the global pooling - bounded loosely."""
+    inputs = c.ins["inputs"].cuda()
+    gold_feats = [c.outs["feat%d" % i] for i in range(len(model.backbone) + 1)]
+    gold_graphs = [c.outs["graph%d" % i].long() for i in range(len(model.backbone) + 1)]
+    with torch.no_grad():
+        ei = model.knn(inputs[:, 0:3])
+        same = (ei[0].cpu().sort(-1).values == gold_graphs[0].sort(-1).values).all(-1)
+        assert same.float().mean() >= 0.99
+        f0 = model.head(inputs, ei).cpu()
+        mask = same.unsqueeze(1).unsqueeze(-1).expand_as(f0)
+        torch.testing.assert_close(f0[mask], gold_feats[0][mask], rtol=RTOL, atol=ATOL)
+        # the head on the reference's graph: no masking needed
+        gold_ei = torch.stack((gold_graphs[0], torch.arange(gold_graphs[0].shape[1]).view(1, -1, 1).expand_as(gold_graphs[0])))
+        torch.testing.assert_close(model.head(inputs, gold_ei.cuda()).cpu(), gold_feats[0], rtol=RTOL, atol=ATOL)
+        for i, blk in enumerate(model.backbone):
+            x_in = gold_feats[i].cuda()
+            g = blk.body.dilated_knn_graph(x_in)[0].cpu()
+            same = (g.sort(-1).values == gold_graphs[i + 1].sort(-1).values).all(-1)
+            assert same.float().mean() >= 0.99, (i, float(same.float().mean()))
+            out = blk(x_in).cpu()
+            mask = same.unsqueeze(1).unsqueeze(-1).expand_as(out)
+            torch.testing.assert_close(out[mask], gold_feats[i + 1][mask], rtol=RTOL, atol=ATOL)
+        y_tail = tail(model, [f.cuda() for f in gold_feats]).cpu()
+        torch.testing.assert_close(y_tail, c.outs["y"], rtol=RTOL, atol=ATOL)
+        y = model(inputs).cpu()
+    err = (y - c.outs["y"]).abs()
+    scale = float(c.outs["y"].abs().max())
+    assert float(err.max()) <= 0.05 * scale, (float(err.max()), scale)
+    assert float((err <= ATOL + RTOL * c.outs["y"].abs()).float().mean()) >= 0.5 or float(err.max()) <= 0.01 * scale
+
+
 def test_resgcn_4_blocks_matches_reference_model():
     """DenseDeepGCN (sem_seg_dense): kNN head on inputs[:, 0:3], EdgeConv head, 3 ResDynBlock2d with dilation
-    1..3 (stochastic dilation in eval = regular dilation + one host RNG draw per layer), fusion, prediction.
-    A single fp32 near-tie in any layer's graph changes that point's neighbour set and, through the later
-    graphs, a few points' outputs: at most 1 % of the (cloud, point) columns may differ beyond tolerance."""
+    1..3 (stochastic dilation in eval = regular dilation + one host RNG draw per layer), fusion, prediction."""
     from bench_models import ResGCN28
     from deep_gcns_torch_b200.gcn_lib import dense as D
     c = gu.load("model_resgcn4")
     m = c.meta
     model = _load_strict(ResGCN28(D, m["in_channels"], m["n_classes"], m["k"], m["n_filters"], m["n_blocks"]), c.sd)
-    with torch.no_grad():
-        torch.manual_seed(5)
-        y = model(c.ins["inputs"].cuda()).cpu()
-    assert y.shape == c.outs["y"].shape
-    bad_cols = ((y - c.outs["y"]).abs() > ATOL + RTOL * c.outs["y"].abs()).any(1)       # (B, N)
-    assert float(bad_cols.float().mean()) <= 0.01, float(bad_cols.float().mean())
+
+    def tail(mod, feats):
+        feats = torch.cat(feats, dim=1)
+        fusion = torch.max_pool2d(mod.fusion_block(feats), kernel_size=[feats.shape[2], feats.shape[3]])
+        fusion = torch.repeat_interleave(fusion, repeats=feats.shape[2], dim=2)
+        return mod.prediction(torch.cat((fusion, feats), dim=1)).squeeze(-1)
+    torch.manual_seed(5)
+    _blockwise(model, c, tail)
 
 
 def test_mrgcn_4_blocks_matches_reference_model():
     """DeepGCN (modelnet_cls): DilatedKnnGraph head (self excluded), MRConv head, 3 ResDynBlock2d('mr') with
     dilation 1..3, fusion + max/avg pooling + prediction."""
+    import torch.nn.functional as F
     from bench_models import MRGCN28
     from deep_gcns_torch_b200.gcn_lib import dense as D
     c = gu.load("model_mrgcn4")
     m = c.meta
     model = _load_strict(MRGCN28(D, m["in_channels"], m["n_classes"], m["k"], m["n_filters"], m["n_blocks"],
                                  m["emb_dims"]), c.sd)
-    with torch.no_grad():
-        y = model(c.ins["inputs"].cuda()).cpu()
-    # global pooling spreads one near-tie flip over every logit: 5e-3 instead of the per-layer 1e-3
-    torch.testing.assert_close(y, c.outs["y"], rtol=5e-3, atol=5e-4)
+
+    def tail(mod, feats):
+        fusion = mod.fusion_block(torch.cat(feats, dim=1))
+        x1, x2 = F.adaptive_max_pool2d(fusion, 1), F.adaptive_avg_pool2d(fusion, 1)
+        return mod.prediction(torch.cat((x1, x2), dim=1)).squeeze(-1).squeeze(-1)
+    _blockwise(model, c, tail)
 
 
 def test_deepergcn_8_layers_res_plus_matches_reference_model():
