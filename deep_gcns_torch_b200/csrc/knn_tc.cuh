@@ -386,8 +386,8 @@ struct TcArgs {
 };
 
 constexpr int TC_THREADS = 128;                       // one warpgroup: thread r = TMEM lane r = query r
-constexpr int TC_FLUSH_AT = 9;                        // flush when any lane of the warp buffered this many (8-byte entries)
-constexpr int TC_BUF = 16;                            // 8-byte slots per thread, >= TC_FLUSH_AT - 1 + 8 (checked every 8 columns)
+constexpr int TC_FLUSH_AT = 1;                        // unpacked (8-byte entries): flush whenever a lane buffered anything
+constexpr int TC_BUF = 16;                            // 8-byte slots per thread, >= TC_FLUSH_AT - 1 + 16 (checked every 16 columns)
 constexpr int TC_FLUSH_EARLY = 10;                    // packed 4-byte entries: 32 slots; tight threshold while the
 constexpr int TC_FLUSH_LATE = 10;                     // list still moves a lot (first tiles), fuller batches afterwards
 constexpr int TC_STAGE_BYTES = TC_PLANES * 2 * TC_MAX_C * 128;   // 32 KB: planes x 2 MN blocks x 64 rows x 128 B
@@ -630,58 +630,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const __grid_cons
       }
     }
     // filter: thread = TMEM lane = query; the accumulator is -key/2 with key = |x_j|^2 - 2 x_i.x_j
-    // (row-constant |x_i|^2 omitted): admit when acc >= -tau/2
+    // (row-constant |x_i|^2 omitted): admit when acc >= -tau/2.  The query itself is an ordinary candidate here
+    // even with exclude_self (it is dropped in the exact re-rank below; the list is 8 entries longer than K) -
+    // a per-thread column patch would turn the chunk registers into an addressable local-memory array.
     const int j0 = tile * TILE;
-    const bool diag = a.exclude_self && j0 == q0;
     const uint32_t tacc = tmem + static_cast<uint32_t>(par * TILE) + lane_base;
     const uint32_t flush_bytes = PACKED ? (tile < 2 ? t.flush_early : t.flush_late) * TC_THREADS * 4u
                                         : TC_FLUSH_AT * TC_THREADS * 8u;
-    // one 16-column chunk: test, buffer, flush when a lane's buffer runs full
-    auto filter16 = [&](uint32_t (&v)[16], int c16) {
-      if (diag && (r >> 4) == c16) {     // self exclusion: only in the diagonal tile, only one column
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i == (r & 15)) v[i] = 0xFF800000u;   // accumulator -inf = key +inf
-      }
-      // PACKED: one LOP3 builds the entry (key & R & I) | (R ^ I) with R = ~0xFFF | index bits 4..11
-      // (tile, chunk) and the immediate I = ~0xFFF | index bits 0..3
-      const uint32_t rbits = 0xFFFFF000u | static_cast<uint32_t>(j0 + c16 * 16);
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        uint32_t jcur = static_cast<uint32_t>(j0 + c16 * 16 + g * 8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t accb = v[g * 8 + i];
-          // if (!(acc < thr_acc)) { buffer[slot] = entry; ++slot; }  - predicated, no branch
-          if (PACKED) {
-            const uint32_t ibits = 0xFFFFF000u | static_cast<uint32_t>(g * 8 + i);
-            asm volatile(
-                "{\n"
-                ".reg .pred p;\n"
-                ".reg .b32 en;\n"
-                "lop3.b32 en, %1, %2, %5, 0xE6;\n"          // (a & b & c) | (b ^ c)
-                "setp.geu.f32 p, %6, %3;\n"
-                "@p st.shared.b32 [%0], en;\n"
-                "@p add.u32 %0, %0, %4;\n"
-                "}"
-                : "+r"(cb_addr)
-                : "r"(accb), "r"(rbits), "f"(thr_acc), "n"(TC_THREADS * 4), "r"(ibits), "f"(__uint_as_float(accb)));
-          } else {
-            asm volatile(
-                "{\n"
-                ".reg .pred p;\n"
-                "setp.geu.f32 p, %1, %3;\n"
-                "@p st.shared.v2.b32 [%0], {%2, %1};\n"
-                "@p add.u32 %0, %0, %4;\n"
-                "}"
-                : "+r"(cb_addr)
-                : "f"(__uint_as_float(accb)), "r"(jcur), "f"(thr_acc), "n"(TC_THREADS * 8));
-            ++jcur;
-          }
-        }
-        if (__any_sync(0xffffffffu, cb_addr - cb_addr0 >= flush_bytes)) flush();
-      }
-    };
     auto poll_issue = [&]() {
       if (to_issue && mbar_test(&sm.mbar_tma, static_cast<uint32_t>(par)) &&
           mbar_test(&sm.mbar_drained, static_cast<uint32_t>(par))) {
@@ -689,6 +644,45 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const __grid_cons
         to_issue = false;
       }
     };
+    // One 16-column chunk: test, buffer, flush when a lane's buffer runs full (checked once per chunk).  A macro, not
+    // a lambda: the body exists once per register buffer and the chunk registers never become an addressable array.
+    // PACKED: one LOP3 builds the entry (key & R & I) | (R ^ I) with R = ~0xFFF | index bits 4..11 (tile, chunk) and
+    // the immediate I = ~0xFFF | index bits 0..3.
+#define DGCN_TC_FILTER16(V, C16)                                                                                      \
+  do {                                                                                                                \
+    const uint32_t rbits = 0xFFFFF000u | static_cast<uint32_t>(j0 + (C16) * 16);                                      \
+    uint32_t jcur = static_cast<uint32_t>(j0 + (C16) * 16);                                                           \
+    _Pragma("unroll") for (int i = 0; i < 16; ++i) {                                                                  \
+      const uint32_t accb = V[i];                                                                                     \
+      /* if (!(acc < thr_acc)) { buffer[slot] = entry; ++slot; }  - predicated, no branch */                          \
+      if (PACKED) {                                                                                                   \
+        const uint32_t ibits = 0xFFFFF000u | static_cast<uint32_t>(i);                                                \
+        asm volatile(                                                                                                 \
+            "{\n"                                                                                                     \
+            ".reg .pred p;\n"                                                                                         \
+            ".reg .b32 en;\n"                                                                                         \
+            "lop3.b32 en, %1, %2, %5, 0xE6;\n" /* (a & b & c) | (b ^ c) */                                            \
+            "setp.geu.f32 p, %6, %3;\n"                                                                               \
+            "@p st.shared.b32 [%0], en;\n"                                                                            \
+            "@p add.u32 %0, %0, %4;\n"                                                                                \
+            "}"                                                                                                       \
+            : "+r"(cb_addr)                                                                                           \
+            : "r"(accb), "r"(rbits), "f"(thr_acc), "n"(TC_THREADS * 4), "r"(ibits), "f"(__uint_as_float(accb)));      \
+      } else {                                                                                                        \
+        asm volatile(                                                                                                 \
+            "{\n"                                                                                                     \
+            ".reg .pred p;\n"                                                                                         \
+            "setp.geu.f32 p, %1, %3;\n"                                                                               \
+            "@p st.shared.v2.b32 [%0], {%2, %1};\n"                                                                   \
+            "@p add.u32 %0, %0, %4;\n"                                                                                \
+            "}"                                                                                                       \
+            : "+r"(cb_addr)                                                                                           \
+            : "f"(__uint_as_float(accb)), "r"(jcur), "f"(thr_acc), "n"(TC_THREADS * 8));                              \
+        ++jcur;                                                                                                       \
+      }                                                                                                               \
+    }                                                                                                                 \
+    if (__any_sync(0xffffffffu, cb_addr - cb_addr0 >= flush_bytes)) flush();                                          \
+  } while (0)
     uint32_t va[16], vb[16];
     __syncwarp();   // tcgen05.ld is warp-collective
     tmem_ld16_async(tacc, va);
@@ -698,13 +692,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const __grid_cons
       __syncwarp();
       tmem_wait16(va);
       tmem_ld16_async(tacc + static_cast<uint32_t>((c16 + 1) * 16), vb);
-      filter16(va, c16);
+      DGCN_TC_FILTER16(va, c16);
       poll_issue();
       __syncwarp();
       tmem_wait16(vb);
       if (c16 + 2 < TILE / 16) tmem_ld16_async(tacc + static_cast<uint32_t>((c16 + 2) * 16), va);
-      filter16(vb, c16 + 1);
+      DGCN_TC_FILTER16(vb, c16 + 1);
     }
+#undef DGCN_TC_FILTER16
     if (to_issue) {   // (thread 0 only) the filter outran the loads: wait, then issue
       mbar_wait(&sm.mbar_tma, static_cast<uint32_t>(par));
       mbar_wait(&sm.mbar_drained, static_cast<uint32_t>(par));
@@ -732,8 +727,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const __grid_cons
     float dex[KP];
 #pragma unroll
     for (int u = 0; u < KP; ++u) {
-      const bool valid = PACKED ? (lk[u] != 0xFFFFFFFFu) : (lk[u] != 0xFFFFFFFFu || lv[u] != 0xFFFFFFFFu);
-      const int j = valid ? static_cast<int>(PACKED ? (lk[u] & 0xFFFu) : lv[u]) : qg;
+      const bool listed = PACKED ? (lk[u] != 0xFFFFFFFFu) : (lk[u] != 0xFFFFFFFFu || lv[u] != 0xFFFFFFFFu);
+      const int j = listed ? static_cast<int>(PACKED ? (lk[u] & 0xFFFu) : lv[u]) : qg;
       const float* xj = xtb + static_cast<int64_t>(j) * C;
       float acc = 0.f;
       if ((C & 7) == 0 && t.xt32) {
@@ -770,9 +765,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const __grid_cons
     int e = 0;
 #pragma unroll
     for (int u = 0; u < KP; ++u) {
-      const bool valid = PACKED ? (lk[u] != 0xFFFFFFFFu) : (lk[u] != 0xFFFFFFFFu || lv[u] != 0xFFFFFFFFu);
-      if (valid) {
-        const uint32_t j = PACKED ? (lk[u] & 0xFFFu) : lv[u];
+      const bool listed = PACKED ? (lk[u] != 0xFFFFFFFFu) : (lk[u] != 0xFFFFFFFFu || lv[u] != 0xFFFFFFFFu);
+      const uint32_t j = PACKED ? (lk[u] & 0xFFFu) : lv[u];
+      if (listed && !(a.exclude_self && j == static_cast<uint32_t>(qg))) {   // self exclusion (DilatedKnnGraph, loop=False)
         const uint64_t key = make_key(dex[u], j);
         int i = e;
         while (i > 0) {

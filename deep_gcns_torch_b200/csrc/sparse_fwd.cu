@@ -69,8 +69,10 @@ __device__ __forceinline__ int chan_of(int lane, int blk, int j) { return blk * 
 // MODE 2: one warp per hub row: merges the row's segment states in segment order, then finishes the row
 //         like MODE 0.  A power-law graph's hubs therefore neither serialise on one warp nor make the
 //         result depend on scheduling.
-template <int VEC, int NBLK, int AGGR, int MODE>
-__global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g) {
+// PRE: the block's norm -> relu is folded into the reads (dgcn_genconv_fusion); a separate instantiation so that
+// the plain kernel keeps its register budget (occupancy is what hides the gather latency).
+template <int VEC, int NBLK, int AGGR, int MODE, bool PRE>
+__global__ void __launch_bounds__(256, PRE ? 3 : 1) genconv_aggregate_kernel(const AggrArgs g) {
   constexpr bool HUB = MODE == 1;
   __shared__ float hub_red[HUB ? 8 : 1][3][VEC][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -86,7 +88,9 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
   } else if (MODE == 1) { row = __ldg(g.hub_items + 2 * hub_it); seg = __ldg(g.hub_items + 2 * hub_it + 1); }
   else { row = __ldg(g.hub_rows + 3 * hub_it); item0 = __ldg(g.hub_rows + 3 * hub_it + 1); nseg = __ldg(g.hub_rows + 3 * hub_it + 2); }
   const int C = g.C;
-  const bool pre = g.pre_scale != nullptr;
+  constexpr bool pre = PRE;
+  // relu(relu(z) + 0) = relu(z): without edge features the message's own relu covers the pre-activation's
+  const bool pre_relu_now = g.pre_relu != 0 && g.edge_attr != nullptr;
   const int rbeg = __ldg(g.rowptr + row), rend = __ldg(g.rowptr + row + 1);
   const int deg = rend - rbeg;
   if (MODE == 0 && g.hub_rows != nullptr && deg >= g.hub_min_degree) return;   // the hub kernels own this row
@@ -137,7 +141,6 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
             }
             if (have[u]) {
               xv[u] = load_vec<VEC>(g.x_src + static_cast<int64_t>(s) * C + cbase);
-              pre_apply<VEC>(xv[u], ps, pt, pre, g.pre_relu != 0);
               if (g.edge_attr) ev[u] = load_vec<VEC>(g.edge_attr + static_cast<int64_t>(ei) * C + cbase);
             }
           }
@@ -147,6 +150,10 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               float v = xv[u].v[j];
+              if (pre) {   // applied here, behind all four row loads, so that the loads stay back to back
+                v = fmaf(ps[j], v, pt[j]);
+                if (pre_relu_now) v = fmaxf(v, 0.f);
+              }
               if (g.edge_attr) v += ev[u].v[j];
               msg[u] = g.raw ? v : fmaxf(v, 0.f) + g.eps;   // torch_vertex.py:85
             }
@@ -324,16 +331,16 @@ __global__ void __launch_bounds__(256) genconv_aggregate_kernel(const AggrArgs g
   }   // hub_it
 }
 
-template <int VEC, int NBLK>
+template <int VEC, int NBLK, bool PRE>
 static int launch_aggr(const AggrArgs& g, cudaStream_t stream) {
   const int warps = 8;
   const unsigned grid = static_cast<unsigned>(ceil_div(g.n_rows, warps));
 #define DGCN_AGGR_CASE(A)                                                                   \
   case A:                                                                                   \
-    if (grid) genconv_aggregate_kernel<VEC, NBLK, A, 0><<<grid, warps * 32, 0, stream>>>(g); \
+    if (grid) genconv_aggregate_kernel<VEC, NBLK, A, 0, PRE><<<grid, warps * 32, 0, stream>>>(g); \
     if (g.hub_rows && g.run_hubs) {                                                                     \
-      genconv_aggregate_kernel<VEC, NBLK, A, 1><<<592, 256, 0, stream>>>(g);                \
-      genconv_aggregate_kernel<VEC, NBLK, A, 2><<<32, 256, 0, stream>>>(g);                 \
+      genconv_aggregate_kernel<VEC, NBLK, A, 1, PRE><<<592, 256, 0, stream>>>(g);                \
+      genconv_aggregate_kernel<VEC, NBLK, A, 2, PRE><<<32, 256, 0, stream>>>(g);                 \
     }                                                                                       \
     break;
   KernelTimer timer(stream, "aggregate");
@@ -450,16 +457,23 @@ int dgcn_genconv_aggregate_fused(const float* x_src, const float* x_dst, int64_t
   const bool aligned = ((reinterpret_cast<uintptr_t>(x_src) | reinterpret_cast<uintptr_t>(x_dst) |
                          reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(edge_attr)) & 15) == 0;
   if ((C % 4) == 0 && aligned) {
-    if (C <= 128) return launch_aggr<4, 1>(g, s);
-    if (C <= 256) return launch_aggr<4, 2>(g, s);
-    if (C <= 512) return launch_aggr<4, 4>(g, s);
-    if (C <= 1024) return launch_aggr<4, 8>(g, s);
+    if (g.pre_scale) {   // fused pre-activation: float4 channel blocks only
+      if (C <= 128) return launch_aggr<4, 1, true>(g, s);
+      if (C <= 256) return launch_aggr<4, 2, true>(g, s);
+      if (C <= 512) return launch_aggr<4, 4, true>(g, s);
+      return DGCN_ERR_UNSUPPORTED;
+    }
+    if (C <= 128) return launch_aggr<4, 1, false>(g, s);
+    if (C <= 256) return launch_aggr<4, 2, false>(g, s);
+    if (C <= 512) return launch_aggr<4, 4, false>(g, s);
+    if (C <= 1024) return launch_aggr<4, 8, false>(g, s);
     return DGCN_ERR_UNSUPPORTED;
   }
-  if (C <= 32) return launch_aggr<1, 1>(g, s);
-  if (C <= 64) return launch_aggr<1, 2>(g, s);
-  if (C <= 128) return launch_aggr<1, 4>(g, s);
-  if (C <= 256) return launch_aggr<1, 8>(g, s);
+  if (g.pre_scale) return DGCN_ERR_UNSUPPORTED;   // C % 4 != 0 or unaligned rows: run the block unfused
+  if (C <= 32) return launch_aggr<1, 1, false>(g, s);
+  if (C <= 64) return launch_aggr<1, 2, false>(g, s);
+  if (C <= 128) return launch_aggr<1, 4, false>(g, s);
+  if (C <= 256) return launch_aggr<1, 8, false>(g, s);
   return DGCN_ERR_UNSUPPORTED;
 }
 

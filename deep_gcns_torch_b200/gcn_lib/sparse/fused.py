@@ -43,7 +43,8 @@ def fusable(conv, norm, h):
     is a single Linear (mlp_layers = 1) and no edge features."""
     return (not torch.is_grad_enabled() and isinstance(norm, nn.BatchNorm1d) and not norm.training and
             norm.running_var is not None and len(conv.mlp) == 1 and isinstance(conv.mlp[0], nn.Linear) and
-            not conv.encode_edge and h.is_cuda and h.dtype == torch.float32)
+            not conv.encode_edge and h.is_cuda and h.dtype == torch.float32 and h.shape[1] % 4 == 0 and
+            h.shape[1] <= 512)
 
 
 def _prm(conv):

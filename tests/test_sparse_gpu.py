@@ -220,7 +220,10 @@ def test_partitioned_layer_emulated_on_one_gpu():
         prm, _k = _native.genconv_params(conv._check_aggr(), tt, pp, yy, conv.eps, conv.msg_norm.msg_scale, True)
         for pre in (None, (s, t, True)):
             z = x if pre is None else torch.relu(x * s + t)
-            full = _native.genconv_aggregate(z, z, _native.csr_build(eic, N), prm)
+            full = _native.genconv_aggregate(x, x, _native.csr_build(eic, N), prm, pre=pre)
+            if pre is not None:      # fused pre-activation == aggregate of the materialised relu(s * x + t)
+                torch.testing.assert_close(full, _native.genconv_aggregate(z, z, _native.csr_build(eic, N), prm),
+                                           rtol=1e-5, atol=1e-6)
             ref = osp.genconv_pre_mlp(z.cpu(), ei, None, aggr, 0.3, 1.5, 0.2, float(conv.msg_norm.msg_scale), 1e-7)
             for part in parts:
                 part.send_rows = torch.empty(0, dtype=torch.int32, device="cuda")     # no NCCL in this test
@@ -233,6 +236,8 @@ def test_partitioned_layer_emulated_on_one_gpu():
                 _native.genconv_aggregate(xbuf, xbuf[:part.n_local], part.csr(), prm, out=out, pre=pre,
                                           rows=part.boundary_rows, skip_hubs=False)
                 assert part.interior_rows.numel() + part.boundary_rows.numel() == part.n_local
+                # same kernel, same per-row edge order: identical bits (the fused pre-activation is evaluated by the
+                # same code on both sides: `full` above also goes through pre=)
                 assert torch.equal(out, full[part.lo:part.hi]), (aggr, pre is not None, part.rank)
             torch.testing.assert_close(full.cpu(), ref, rtol=RTOL, atol=ATOL)
     assert parts[0].interior_rows.numel() > 0 and parts[0].boundary_rows.numel() > 0
