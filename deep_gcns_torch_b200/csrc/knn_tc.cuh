@@ -388,8 +388,8 @@ struct TcArgs {
 constexpr int TC_THREADS = 128;                       // one warpgroup: thread r = TMEM lane r = query r
 constexpr int TC_FLUSH_AT = 1;                        // unpacked (8-byte entries): flush whenever a lane buffered anything
 constexpr int TC_BUF = 16;                            // 8-byte slots per thread, >= TC_FLUSH_AT - 1 + 16 (checked every 16 columns)
-constexpr int TC_FLUSH_EARLY = 10;                    // packed 4-byte entries: 32 slots; tight threshold while the
-constexpr int TC_FLUSH_LATE = 10;                     // list still moves a lot (first tiles), fuller batches afterwards
+constexpr int TC_FLUSH_EARLY = 16;                    // packed 4-byte entries: 32 slots; tight threshold while the
+constexpr int TC_FLUSH_LATE = 16;                     // list still moves a lot (first tiles), fuller batches afterwards
 constexpr int TC_STAGE_BYTES = TC_PLANES * 2 * TC_MAX_C * 128;   // 32 KB: planes x 2 MN blocks x 64 rows x 128 B
 constexpr int TC_XBLOCK_BYTES = 2 * 16 * 128;                    // 4 KB: one extra K=16 block, 2 MN blocks x 16 rows x 128 B
 constexpr int TC_ISSUE_CHUNK = 2;                                 // 32-column chunk of tile t before which the MMAs of tile t+1 are issued
@@ -719,47 +719,60 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const __grid_cons
   const int C = a.C;
   const float* xtb = t.xt + static_cast<int64_t>(b) * N * C;
   {
-    float xq[TC_MAX_C];
-#pragma unroll
-    for (int c = 0; c < TC_MAX_C; ++c) xq[c] = c < C ? __ldg(xtb + static_cast<int64_t>(qg) * C + c) : 0.f;
-    // pass 1: exact distances of all listed candidates - pure loads + FMA chains, no shared-memory
-    // traffic in between, so the loads of the next candidates overlap the chains of the current one
+    // pass 1: exact distances of all listed candidates.  Channels in chunks of 8 in the OUTER loop, candidates in
+    // the inner one: every candidate keeps its own accumulator, so KP independent FMA chains are in flight (a single
+    // 64-long chain per candidate would expose the FMA latency 64 times) and only 8 query channels are live at a
+    // time.  Per candidate the chain is still acc = fma(x_q[c], x_j[c], acc) for c ascending from acc = 0 - the bits
+    // of the fp32 kernel.
     float dex[KP];
+    uint32_t off[KP];                 // element offset of the candidate's row in the node-major copy
 #pragma unroll
     for (int u = 0; u < KP; ++u) {
       const bool listed = PACKED ? (lk[u] != 0xFFFFFFFFu) : (lk[u] != 0xFFFFFFFFu || lv[u] != 0xFFFFFFFFu);
-      const int j = listed ? static_cast<int>(PACKED ? (lk[u] & 0xFFFu) : lv[u]) : qg;
-      const float* xj = xtb + static_cast<int64_t>(j) * C;
-      float acc = 0.f;
-      if ((C & 7) == 0 && t.xt32) {
-        // one 256-bit load per 8 channels: each lane reads a different row, so every load is its own
-        // L1 wavefront - half as many as with 128-bit loads
+      const uint32_t j = listed ? (PACKED ? (lk[u] & 0xFFFu) : lv[u]) : static_cast<uint32_t>(qg);
+      off[u] = j * static_cast<uint32_t>(C);
+      dex[u] = 0.f;
+    }
+    const float* xqp = xtb + static_cast<int64_t>(qg) * C;
+    if ((C & 7) == 0 && t.xt32) {
+      // one 256-bit load per 8 channels: each lane reads a different row, so every load is its own L1 wavefront
+#pragma unroll 1
+      for (int c = 0; c < C; c += 8) {
+        float q8[8];
+        ldg256(xqp + c, q8);
 #pragma unroll
-        for (int c = 0; c < TC_MAX_C; c += 8) {
-          if (c < C) {
-            float w[8];
-            ldg256(xj + c, w);
+        for (int u = 0; u < KP; ++u) {
+          float w[8];
+          ldg256(xtb + off[u] + c, w);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc = fmaf(xq[c + i], w[i], acc);
-          }
+          for (int i = 0; i < 8; ++i) dex[u] = fmaf(q8[i], w[i], dex[u]);
         }
-      } else if ((C & 3) == 0) {
-#pragma unroll
-        for (int c = 0; c < TC_MAX_C; c += 4) {
-          if (c < C) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(xj + c));
-            acc = fmaf(xq[c], w.x, acc);
-            acc = fmaf(xq[c + 1], w.y, acc);
-            acc = fmaf(xq[c + 2], w.z, acc);
-            acc = fmaf(xq[c + 3], w.w, acc);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < TC_MAX_C; ++c)
-          if (c < C) acc = fmaf(xq[c], __ldg(xj + c), acc);
       }
-      dex[u] = (sqq + (-2.0f * acc)) + __ldg(sqb + j);
+    } else if ((C & 3) == 0) {
+#pragma unroll 1
+      for (int c = 0; c < C; c += 4) {
+        const float4 q4 = __ldg(reinterpret_cast<const float4*>(xqp + c));
+#pragma unroll
+        for (int u = 0; u < KP; ++u) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(xtb + off[u] + c));
+          dex[u] = fmaf(q4.x, w.x, dex[u]);
+          dex[u] = fmaf(q4.y, w.y, dex[u]);
+          dex[u] = fmaf(q4.z, w.z, dex[u]);
+          dex[u] = fmaf(q4.w, w.w, dex[u]);
+        }
+      }
+    } else {
+      for (int c = 0; c < C; ++c) {
+        const float q1 = __ldg(xqp + c);
+#pragma unroll
+        for (int u = 0; u < KP; ++u) dex[u] = fmaf(q1, __ldg(xtb + off[u] + c), dex[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < KP; ++u) {
+      const bool listed = PACKED ? (lk[u] != 0xFFFFFFFFu) : (lk[u] != 0xFFFFFFFFu || lv[u] != 0xFFFFFFFFu);
+      const uint32_t j = listed ? (PACKED ? (lk[u] & 0xFFFu) : lv[u]) : static_cast<uint32_t>(qg);
+      dex[u] = (sqq + (-2.0f * dex[u])) + __ldg(sqb + j);
     }
     // pass 2: insertion by exact key into the exact-sorted prefix [0, e)
     int e = 0;

@@ -25,6 +25,16 @@ def _frac_bad(got, ref):
     return float(((got - ref).abs() > ATOL + RTOL * ref.abs()).float().mean())
 
 
+@pytest.fixture(autouse=True)
+def _ieee_fp32_convolutions():
+    """The model tails (fusion / prediction BasicConv heads) are plain torch Conv2d modules, exactly the reference's;
+    torch runs cuDNN convolutions in TF32 by default (1e-3 relative), the CPU golden is fp32 - compare like with like."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
 def _blockwise(model, c, tail):
     """Every stage of the model on the REFERENCE's own stage input (no error accumulation): graph adjudicated
     as a set per (cloud, point) row, features compared on the rows whose neighbour set agrees (a row differs
