@@ -82,10 +82,11 @@ def sparse_halo_block(dev, rank, world, layers=112, parity_layers=4, num_nodes=P
            "N": num_nodes, "E": num_edges, "partition": "contiguous destination-row ranges x%d" % world}
     torch.manual_seed(0)
     model = DeeperGCN(S, layers=layers, hidden=HIDDEN, in_channels=HIDDEN, tasks=40).to(dev).eval()
+    halo_group = P.high_priority_group()          # the exchange must not queue behind the aggregate's CTAs
     for kind in ("block", "uniform"):
         src, dst = local_edges(num_nodes, num_edges, rank, world, kind, dev)
         t0 = time.perf_counter()
-        part = P.GraphPartition.from_local_edges(src, dst, num_nodes, rank, world, dev).exchange_halo_lists()
+        part = P.GraphPartition.from_local_edges(src, dst, num_nodes, rank, world, dev).exchange_halo_lists(halo_group)
         part.csr()
         torch.cuda.synchronize()
         build_ms = (time.perf_counter() - t0) * 1e3
@@ -116,7 +117,7 @@ def sparse_halo_block(dev, rank, world, layers=112, parity_layers=4, num_nodes=P
             # the whole stack: aggregate + Linear + skip per layer, as the model runs it
             model_ms = _time_ms(lambda: model.forward_partitioned(x_local, part), 2, sync)
             # ---- parity: first `parity_layers` layers against the single-GPU full-graph forward -----------
-            h_part = model.forward_partitioned(x_local, part, layers=parity_layers, head=False)
+            h_part = model.forward_partitioned(x_local, part, layers=parity_layers, head=False).clone()   # (a view of the persistent buffer)
             finite = bool(torch.isfinite(model.forward_partitioned(x_local, part)).all())
             g = torch.Generator(device=dev).manual_seed(99)
             rows = torch.randint(0, part.n_local, (sample_rows,), generator=g, device=dev)

@@ -26,6 +26,17 @@ import torch
 import torch.distributed as dist
 
 
+def high_priority_group(ranks=None):
+    """A NCCL process group whose kernels run on a high-priority stream: a halo all-to-all launched next to a
+    grid-filling aggregate kernel is scheduled as CTAs retire instead of after the whole grid has been dispatched.
+    (gloo / single process: the default group.)"""
+    if not dist.is_initialized() or dist.get_backend() != "nccl":
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True
+    return dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+
+
 def row_ranges(num_nodes, world):
     """Contiguous, balanced row ranges [(lo, hi)] * world."""
     base, rem = divmod(num_nodes, world)
@@ -87,6 +98,7 @@ class GraphPartition:
         self._csr = None
         self._buffers = {}
         self._comm_stream = None
+        self.group = None
 
     # ---- one-time setup --------------------------------------------------------------------------
     def exchange_halo_lists(self, group=None):
@@ -106,6 +118,7 @@ class GraphPartition:
         dist.all_to_all_single(recv, want.to(comm_dev), output_split_sizes=self.send_counts,
                                input_split_sizes=self.recv_counts, group=group)
         self.send_rows = recv.to(self.device, torch.int32)          # local row ids, grouped by destination rank
+        self.group = group                                          # the exchanges of this partition use it too
         return self
 
     def csr(self):
@@ -132,7 +145,7 @@ class GraphPartition:
 
     def comm_stream(self):
         if self._comm_stream is None:
-            self._comm_stream = torch.cuda.Stream(self.device)
+            self._comm_stream = torch.cuda.Stream(self.device, priority=-1)      # ahead of the aggregate's grid
         return self._comm_stream
 
     def halo_bytes(self, channels):
@@ -158,6 +171,7 @@ def start_halo_exchange(part, channels, slot=0, group=None):
     returns a handle whose wait() makes the CURRENT stream wait for the halo.  CPU (gloo): synchronous."""
     xbuf, send = part.buffers(channels, slot)
     local, halo = xbuf[:part.n_local], xbuf[part.n_local:]
+    group = group if group is not None else part.group
     if not xbuf.is_cuda:
         _pack(local, part.send_rows, out=send)
         dist.all_to_all_single(halo, send, output_split_sizes=part.recv_counts, input_split_sizes=part.send_counts,
@@ -177,6 +191,7 @@ def start_halo_exchange(part, channels, slot=0, group=None):
 def halo_exchange(x_local, part, gather=None, group=None):
     """[local rows | halo rows] as a NEW tensor (simple, allocation per call): packs the rows the peers asked
     for and swaps them all-to-all.  The persistent-buffer path is start_halo_exchange()."""
+    group = group if group is not None else part.group
     send = gather(x_local, part.send_rows) if gather is not None else _pack(x_local, part.send_rows)
     recv = torch.empty((part.n_halo, x_local.shape[1]), dtype=x_local.dtype, device=x_local.device)
     dist.all_to_all_single(recv, send, output_split_sizes=part.recv_counts, input_split_sizes=part.send_counts,
@@ -200,7 +215,7 @@ class HaloExchange(torch.autograd.Function):
         g_halo = grad[part.n_local:].contiguous()
         back = torch.empty((int(part.send_rows.numel()), grad.shape[1]), dtype=grad.dtype, device=grad.device)
         dist.all_to_all_single(back, g_halo, output_split_sizes=part.send_counts, input_split_sizes=part.recv_counts,
-                               group=ctx.group)
+                               group=ctx.group if ctx.group is not None else part.group)
         g_local.index_add_(0, part.send_rows.long(), back)
         return g_local, None, None
 

@@ -23,7 +23,7 @@ def main():
     ei = torch.randint(0, N, (2, E), generator=g)
     ei[1, :5000] = 17                                  # one hub row (segmented CTA path) on rank 0
     x = torch.randn(N, C, generator=g)
-    part = P.GraphPartition(ei.to(dev), N, rank, world, device=dev).exchange_halo_lists()
+    part = P.GraphPartition(ei.to(dev), N, rank, world, device=dev).exchange_halo_lists(P.high_priority_group())
     lo, hi = part.lo, part.hi
     for aggr in ("softmax_sg", "power", "max"):
         torch.manual_seed(1)
