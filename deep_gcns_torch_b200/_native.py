@@ -103,6 +103,10 @@ def _declare(lib):
     lib.dgcn_genconv_aggregate_fused.restype = ctypes.c_int
     lib.dgcn_genconv_aggregate_fused.argtypes = [vp, vp, c_i64, c_i64, vp, vp, vp, vp, ctypes.POINTER(GenconvParamsC),
                                                  ctypes.POINTER(CsrHubsC), ctypes.POINTER(GenconvFusionC), vp, vp]
+    lib.dgcn_linear_residual_workspace_bytes.restype = sz
+    lib.dgcn_linear_residual_workspace_bytes.argtypes = [c_i64, c_i64]
+    lib.dgcn_linear_residual.restype = ctypes.c_int
+    lib.dgcn_linear_residual.argtypes = [vp, c_i64, c_i64, vp, vp, c_i64, vp, vp, vp, sz, vp]
     lib.dgcn_csr_hub_rows.restype = ctypes.c_int
     lib.dgcn_csr_hub_rows.argtypes = [vp, c_i64, c_i64, c_i32, c_i32, vp, vp, vp, vp]
     lib.dgcn_genconv_aggregate_backward.restype = ctypes.c_int
@@ -457,6 +461,32 @@ def genconv_aggregate_backward(x_src, x_dst, csr, prm, grad_out, edge_attr=None,
                                                    _ptr(gea), _ptr(gsc), _stream(dev))
         _check(rc, "dgcn_genconv_aggregate_backward")
     return gsrc, gdst, gea, gsc
+
+
+def linear_residual_supported(K, M):
+    return lib().dgcn_linear_residual_workspace_bytes(int(K), int(M)) > 0
+
+
+def linear_residual(a, weight, bias=None, res=None, out=None):
+    """dgcn_linear_residual: out (N, M) = a @ weight^T (+ bias) (+ res) on the tcgen05 tensor cores."""
+    _require_cuda(a, weight, bias, res, out)
+    a, weight, bias, res = _f32(a), _f32(weight), _f32(bias), _f32(res)
+    N, K = a.shape
+    M = weight.shape[0]
+    dev = a.device
+    with torch.cuda.device(dev):
+        l = lib()
+        nbytes = l.dgcn_linear_residual_workspace_bytes(K, M)
+        if nbytes == 0:
+            raise RuntimeError("dgcn_linear_residual: unsupported shape K=%d M=%d" % (K, M))
+        if out is None:
+            out = torch.empty((N, M), dtype=torch.float32, device=dev)
+        elif out.shape != (N, M) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise RuntimeError("linear_residual: out must be a contiguous fp32 (N, M) tensor")
+        ws = _workspace(nbytes, dev)
+        _check(l.dgcn_linear_residual(_ptr(a), N, K, _ptr(weight), _ptr(bias), M, _ptr(res), _ptr(out), _ptr(ws),
+                                      ws.numel(), _stream(dev)), "dgcn_linear_residual")
+    return out
 
 
 def gather_rows(x, rows, out=None):

@@ -290,7 +290,7 @@ __device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N, k = a.k;
   constexpr int QPW = TILE / NW;            // queries per warp
-  static_assert(QPW == 32, "wide consumer: one warp per 32 queries");
+  static_assert(QPW == 32 || QPW == 16, "wide consumer: a warp owns 32 or 16 queries (8 | QPW / (32 / G) for G = 16, 32)");
   const int64_t node0 = static_cast<int64_t>(b) * N;
   for (int qq = 0; qq < QPW; ++qq) {
     const int ql = warp * QPW + qq;

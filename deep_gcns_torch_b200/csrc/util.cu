@@ -11,6 +11,7 @@ static thread_local char g_last_error[512] = "";
 void set_last_cuda_error(cudaError_t e, const char* file, int line) {
   snprintf(g_last_error, sizeof(g_last_error), "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file,
            line);
+  (void)cudaGetLastError();   // reported through the status code: do not leave it for an unrelated later launch check
 }
 
 struct TimedLaunch {

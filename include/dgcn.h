@@ -253,6 +253,19 @@ int dgcn_genconv_aggregate_fused(const float* x_src, const float* x_dst, int64_t
                                  const dgcn_genconv_fusion* fus /* may be NULL */, float* out,
                                  dgcn_stream_t stream);
 
+/* Row-wise Linear with fused bias and skip connection on the tcgen05 tensor cores:
+ *   out[n][m] = sum_k a[n][k] * weight[m][k] (+ bias[m]) (+ res[n][m])
+ * = the Linear that ends GENConv's MLP (gcn_lib/sparse/torch_nn.py:56-68 with mlp_layers = 1; nn.Linear
+ * weight layout (M, K)) plus the `+ h` of DeeperGCN's res+ block (examples/ogb/ogbn_arxiv/model.py:104).
+ * fp32 in / out; the product runs as a two-plane bf16 split of both operands (4 tensor-core products, fp32
+ * accumulation in TMEM, error <= ~2^-16 * sum_k |a||w|).  K in {64, 128, 256}, M a multiple of 32 up to 256,
+ * 16-byte aligned rows; anything else returns DGCN_ERR_UNSUPPORTED (callers keep cuBLAS for those).
+ * bias, res may be NULL; out may alias res.  ws: dgcn_linear_residual_workspace_bytes(K, M) (0 = unsupported). */
+size_t dgcn_linear_residual_workspace_bytes(int64_t K, int64_t M);
+int dgcn_linear_residual(const float* a, int64_t N, int64_t K, const float* weight, const float* bias,
+                         int64_t M, const float* res, float* out, void* ws, size_t ws_bytes,
+                         dgcn_stream_t stream);
+
 /* Gradient of dgcn_genconv_aggregate w.r.t. x (both roles), edge_attr and the
  * scalar parameters.  The softmax weights carry gradient only when
  * softmax_grad != 0 (reference: learn_t, torch_message.py:51-55).

@@ -61,7 +61,10 @@ def main():
             continue
         gsum = p.grad.clone()
         dist.all_reduce(gsum)                          # parameter gradients add up over the row partitions
-        torch.testing.assert_close(gsum, ref_gp[n], rtol=2e-3, atol=2e-4, msg=n)
+        # sums of ~20k row products: compare at the scale of the gradient, not of its smallest entries
+        scale = float(ref_gp[n].abs().max())
+        torch.testing.assert_close(gsum, ref_gp[n], rtol=2e-3, atol=2e-4 * max(scale, 1.0),
+                                   msg=lambda m, n=n: "%s: %s" % (n, m))
     dist.barrier()
     if rank == 0:
         print("MULTIGPU_SPARSE_OK world=%d halo_rows=%d interior=%d boundary=%d" %

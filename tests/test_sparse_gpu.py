@@ -241,3 +241,32 @@ def test_partitioned_layer_emulated_on_one_gpu():
                 assert torch.equal(out, full[part.lo:part.hi]), (aggr, pre is not None, part.rank)
             torch.testing.assert_close(full.cpu(), ref, rtol=RTOL, atol=ATOL)
     assert parts[0].interior_rows.numel() > 0 and parts[0].boundary_rows.numel() > 0
+
+
+@pytest.mark.parametrize("N,K,M", [(1000, 128, 128), (129, 64, 32), (5000, 256, 64), (3000, 64, 256), (128 * 150 + 7, 128, 64), (1, 64, 96)])
+def test_tcgen05_row_linear_with_bias_and_skip(N, K, M):
+    """dgcn_linear_residual (tcgen05, two-plane bf16 split of both operands) against an fp64 Linear: the split
+    leaves <= ~2^-16 * sum|a||w| of error, far inside the 1e-3 parity tolerance; bias / skip optional; rows beyond
+    the last full 128-row tile; out aliasing res."""
+    from deep_gcns_torch_b200 import _native
+    g = torch.Generator().manual_seed(N + K + M)
+    a = (torch.randn(N, K, generator=g) * 3).cuda()
+    w = torch.randn(M, K, generator=g).cuda() / K ** 0.5
+    b = torch.randn(M, generator=g).cuda()
+    h = torch.randn(N, M, generator=g).cuda()
+    mag = a.double().abs() @ w.double().abs().t()                      # sum_k |a||w| per output
+    for bias, res in ((b, h), (None, h), (b, None), (None, None)):
+        ref = a.double() @ w.double().t()
+        if bias is not None:
+            ref = ref + bias.double()
+        if res is not None:
+            ref = ref + res.double()
+        out = _native.linear_residual(a, w, bias, res)
+        err = (out.double() - ref).abs()
+        assert bool((err <= 4e-5 * mag + 1e-6 * ref.abs() + 1e-6).all()), float((err / (mag + 1e-9)).max())
+        torch.testing.assert_close(out, ref.float(), rtol=1e-3, atol=1e-4)
+    buf = h.clone()
+    _native.linear_residual(a, w, b, buf, out=buf)                     # in place on the skip tensor
+    torch.testing.assert_close(buf, (a.double() @ w.double().t() + b.double() + h.double()).float(), rtol=1e-3, atol=1e-4)
+    assert not _native.linear_residual_supported(100, 128) and not _native.linear_residual_supported(128, 300)
+    assert not _native.linear_residual_supported(256, 256)            # operands would not fit one SM's shared memory
