@@ -40,10 +40,29 @@ size_t knn_workspace_bytes(int64_t B, int64_t C, int64_t N, int64_t K) {
   }
   if (K > SMALL_K_MAX) {
     const int64_t ldd = (N + 3) / 4 * 4;
-    bytes += align_up(knn_slab_clouds(B, N) * N * ldd * 4, 256);
+    const size_t nslab = static_cast<size_t>(B) > knn_slab_clouds(B, N) ? 2 : 1;   // two slabs: distance rows of slab s+1 overlap the select of slab s
+    bytes += nslab * align_up(knn_slab_clouds(B, N) * N * ldd * 4, 256);
     bytes += align_up(knn_slab_clouds(B, N) * N * 4 + 256, 256);   // rows the sampled select hands to the exact kernel
   }
   return bytes + 256;
+}
+
+// Side stream of the large-K slab pipeline, one per device, created on first use (a write-once cache: the stream
+// carries no state between calls - every call forks it from and joins it back into the caller's stream by events).
+static cudaStream_t slab_side_stream() {
+  static std::atomic<cudaStream_t> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  cudaStream_t s = cached[dev].load(std::memory_order_acquire);
+  if (!s) {
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaStream_t expected = nullptr;
+    if (!cached[dev].compare_exchange_strong(expected, s, std::memory_order_acq_rel)) {
+      cudaStreamDestroy(s);
+      s = expected;
+    }
+  }
+  return s;
 }
 
 static int next_pow2(int v) {
@@ -197,7 +216,9 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
   if (K > LARGE_K_MAX) return DGCN_ERR_UNSUPPORTED;
   const int ldd = (N + 3) / 4 * 4;
   const int nbmax = static_cast<int>(knn_slab_clouds(B, N));
-  float* drows = ws.take<float>(static_cast<size_t>(nbmax) * N * ldd);
+  const size_t slab_elems = static_cast<size_t>(nbmax) * N * ldd;
+  float* drows = ws.take<float>(slab_elems);
+  float* drows2 = B > nbmax ? ws.take<float>(slab_elems) : nullptr;   // second slab: distance rows run one slab ahead
   if (!ws.ok) return DGCN_ERR_WORKSPACE;
   const int KP = next_pow2(K);
   const size_t per_warp = static_cast<size_t>(KP) * 8 + static_cast<size_t>(ldd) * 4 + static_cast<size_t>((a.k + 31) / 32 * 32) * 4;   // ldd = N rounded up to 4 keeps every warp's u64 array 16-byte aligned
@@ -232,23 +253,55 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
     DGCN_ENSURE_SMEM((select_rows_fast_kernel), smem_f);
   }
   KernelTimer timer(stream, "knn");
-  for (int b0 = 0; b0 < B; b0 += nbmax) {
+  // Two-stream slab pipeline: the FMA-bound distance rows of slab s+1 (side stream) run under the latency-bound
+  // per-row select of slab s (caller's stream); events fork the side stream from the caller's stream and join it
+  // back, so the call is still one stream-ordered operation for the caller (and capturable in a CUDA graph).
+  cudaStream_t side = drows2 ? slab_side_stream() : nullptr;
+  cudaEvent_t ev_dist[2] = {nullptr, nullptr}, ev_sel[2] = {nullptr, nullptr}, ev_start = nullptr;
+  if (side) {
+    bool okev = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && okev; ++i)
+      okev = cudaEventCreateWithFlags(&ev_dist[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ev_sel[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!okev) side = nullptr;
+  }
+  struct EventGuard {   // destroying an event that is still in flight is legal: it is released on completion
+    cudaEvent_t* e[5];
+    ~EventGuard() { for (cudaEvent_t* p : e) if (p && *p) cudaEventDestroy(*p); }
+  } guard{{&ev_start, &ev_dist[0], &ev_dist[1], &ev_sel[0], &ev_sel[1]}};
+  if (side) {
+    DGCN_CUDA_TRY(cudaEventRecord(ev_start, stream));
+    DGCN_CUDA_TRY(cudaStreamWaitEvent(side, ev_start, 0));
+  }
+  int slab = 0;
+  for (int b0 = 0; b0 < B; b0 += nbmax, ++slab) {
     const int nb = (B - b0 < nbmax) ? (B - b0) : nbmax;
-    dist_rows_kernel<<<dim3(ceil_div(N, TILE), ceil_div(N, TILE), nb), NTHREADS, 0, stream>>>(a, b0, drows, ldd);
-    DGCN_LAUNCH_CHECK();
+    const int buf = side ? (slab & 1) : 0;
+    float* drows_s = buf ? drows2 : drows;
+    if (side) {
+      if (slab >= 2) DGCN_CUDA_TRY(cudaStreamWaitEvent(side, ev_sel[buf], 0));   // the select two slabs back has left this buffer
+      dist_rows_kernel<<<dim3(ceil_div(N, TILE), ceil_div(N, TILE), nb), NTHREADS, 0, side>>>(a, b0, drows_s, ldd);
+      DGCN_LAUNCH_CHECK();
+      DGCN_CUDA_TRY(cudaEventRecord(ev_dist[buf], side));
+      DGCN_CUDA_TRY(cudaStreamWaitEvent(stream, ev_dist[buf], 0));
+    } else {
+      dist_rows_kernel<<<dim3(ceil_div(N, TILE), ceil_div(N, TILE), nb), NTHREADS, 0, stream>>>(a, b0, drows_s, ldd);
+      DGCN_LAUNCH_CHECK();
+    }
     const int64_t rows = static_cast<int64_t>(nb) * N;
     if (fast) {
       DGCN_CUDA_TRY(cudaMemsetAsync(rowlist, 0, 256, stream));
       select_rows_fast_kernel<<<static_cast<unsigned>(ceil_div(rows, warps_f)), warps_f * 32, smem_f, stream>>>(
-          a, b0, nb, drows, ldd, cap, sample_rank, warps_f, rowlist, rowlist + 64);
+          a, b0, nb, drows_s, ldd, cap, sample_rank, warps_f, rowlist, rowlist + 64);
       DGCN_LAUNCH_CHECK();
-      select_rows_kernel<<<296, warps * 32, smem, stream>>>(a, b0, nb, drows, ldd, KP, ldd, warps, rowlist + 64, rowlist);
+      select_rows_kernel<<<296, warps * 32, smem, stream>>>(a, b0, nb, drows_s, ldd, KP, ldd, warps, rowlist + 64, rowlist);
       DGCN_LAUNCH_CHECK();
     } else {
       select_rows_kernel<<<static_cast<unsigned>(ceil_div(rows, warps)), warps * 32, smem, stream>>>(
-          a, b0, nb, drows, ldd, KP, ldd, warps, nullptr, nullptr);
+          a, b0, nb, drows_s, ldd, KP, ldd, warps, nullptr, nullptr);
       DGCN_LAUNCH_CHECK();
     }
+    if (side) DGCN_CUDA_TRY(cudaEventRecord(ev_sel[buf], stream));
   }
   return DGCN_OK;
 }
