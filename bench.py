@@ -320,6 +320,48 @@ def gpu_reference_block(dev, steps, warmup):
                     "inputs resident, peak memory ~5 GB (B x N x N distance matrix + gathered edge features)"}
 
 
+def sparse_aggregate_block(dev, steps=10):
+    """GENConv softmax aggregate (message + online softmax + residual, one fused kernel) on a synthetic
+    ogbn-products-shaped CSR (N = 2,449,029, E = 61,859,140 uniform edges, C = 128; x = 1.25 GB >> L2), against the
+    gather-model HBM roofline of SURVEY.md 8d: 4C+4 B/edge + (8C+4) B/node.  Target (north_star): >= 60 % of the
+    measured HBM peak.  L2 is flushed between iterations."""
+    import torch
+    from deep_gcns_torch_b200 import _native
+    N, E, C = 2449029, 61859140, 128
+    g = torch.Generator(device=dev).manual_seed(0)
+    ei = torch.stack((torch.randint(0, N, (E,), generator=g, device=dev), torch.randint(0, N, (E,), generator=g, device=dev)))
+    x = torch.randn(N, C, generator=g, device=dev)
+    csr = _native.csr_build(ei, N)
+    del ei
+    prm, _keep = _native.genconv_params("softmax_sg", 0.1, 1.0, 0.0, 1e-7, None, add_residual=True)
+    out = torch.empty_like(x)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        _native.genconv_aggregate(x, x, csr, prm, out=out)
+    times = []
+    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(steps):
+        flush.zero_()
+        beg.record()
+        _native.genconv_aggregate(x, x, csr, prm, out=out)
+        end.record()
+        torch.cuda.synchronize()
+        times.append(beg.elapsed_time(end))
+    times.sort()
+    ms = times[len(times) // 2]
+    peak = peaks()[0]
+    gather_bytes = E * (4 * C + 4) + N * (8 * C + 4)
+    res = {"workload": "GENConv aggregate softmax_sg t=0.1, N=%d E=%d C=%d (products-shaped, uniform)" % (N, E, C),
+           "ms": ms, "edges_per_s": E / (ms * 1e-3), "steps": steps,
+           "roofline": {"bound": "hbm", "achieved": gather_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": gather_bytes / (ms * 1e-3) / 1e9 / peak, "bytes_per_launch": gather_bytes,
+                        "model": "gather model: 4C+4 B/edge + (8C+4) B/node (SURVEY.md 8d); ncu dram bytes of the same "
+                                 "launch: profiles/r02_aggregate_products_ncu.json"}}
+    del x, out, flush, csr
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -425,8 +467,14 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
-    # ---- multi-GPU blocks (outside the headline's timed regions): config 5 and config 4 ---------------------
+    # ---- N = 1: the sparse hot kernel against its HBM roofline on the products-shaped CSR (outside the timed regions) ----
     extra = None
+    if world == 1 and not args.no_extra:
+        try:
+            extra = {"sparse_aggregate": sparse_aggregate_block(dev)}
+        except Exception as exc:
+            extra = {"sparse_aggregate": {"error": "%s: %s" % (type(exc).__name__, exc)}}
+    # ---- multi-GPU blocks (outside the headline's timed regions): config 5 and config 4 ---------------------
     if world > 1 and not args.no_extra:
         import bench_multigpu as bm
         extra = {}

@@ -57,6 +57,11 @@ class GenconvParamsC(ctypes.Structure):
                 ("add_residual", c_i32), ("raw_message", c_i32)]
 
 
+class BlockFusionC(ctypes.Structure):
+    _fields_ = [("residual", c_f32p), ("res_stride_b", c_i64), ("res_stride_c", c_i64), ("res_scale", ctypes.c_float),
+                ("out_stride_b", c_i64)]
+
+
 class GenconvFusionC(ctypes.Structure):
     _fields_ = [("pre_scale", c_f32p), ("pre_shift", c_f32p), ("pre_relu", c_i32), ("skip_hubs", c_i32),
                 ("row_list", ctypes.c_void_p), ("n_rows", c_i64)]
@@ -87,6 +92,10 @@ def _declare(lib):
     lib.dgcn_dyn_conv_forward.restype = ctypes.c_int
     lib.dgcn_dyn_conv_forward.argtypes = [c_i32, vp, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(DilationC),
                                           ctypes.POINTER(BasicConvC), c_i64, vp, vp, vp, sz, vp]
+    lib.dgcn_dyn_conv_forward_fused.restype = ctypes.c_int
+    lib.dgcn_dyn_conv_forward_fused.argtypes = [c_i32, vp, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(DilationC),
+                                                ctypes.POINTER(BasicConvC), c_i64, vp, vp, ctypes.POINTER(BlockFusionC),
+                                                vp, sz, vp]
     lib.dgcn_graph_conv_backward_workspace_bytes.restype = sz
     lib.dgcn_graph_conv_backward_workspace_bytes.argtypes = [c_i32] + [c_i64] * 5
     lib.dgcn_graph_conv_backward.restype = ctypes.c_int
@@ -277,9 +286,12 @@ def graph_conv_forward(conv, x, prm, edge_index=None, nbr=None):
     return out
 
 
-def dyn_conv_forward(conv, x, prm, k, dilation=1, cols=None, want_nbr=False):
-    """dgcn_dyn_conv_forward: (out (B, C_out, N, 1), nbr (B,N,k) int32 | None)."""
-    _require_cuda(x, *prm.tensors())
+def dyn_conv_forward(conv, x, prm, k, dilation=1, cols=None, want_nbr=False, residual=None, res_scale=1.0, out=None):
+    """dgcn_dyn_conv_forward(_fused): (out (B, C_out, N, 1), nbr (B,N,k) int32 | None).
+
+    residual (B, C_out, N[, 1]): out = conv + residual * res_scale (ResDynBlock2d); out: write into this tensor, which
+    may be a channel slice of a wider (B, C_total, N, 1) buffer (inference only, no train-mode BatchNorm)."""
+    _require_cuda(x, residual, out, *prm.tensors())
     x3, B, C, N, sb, sc = _dense_view(x)
     K = int(k) * int(dilation)
     if K > N:
@@ -290,11 +302,26 @@ def dyn_conv_forward(conv, x, prm, k, dilation=1, cols=None, want_nbr=False):
         l = lib()
         cs = prm.c_struct(dev)
         dil, keep = _dilation(k, dilation, cols)
-        out = torch.empty((B, c_out, N, 1), dtype=torch.float32, device=dev)
+        fus = None
+        if residual is not None or out is not None:
+            fus = BlockFusionC()
+            if residual is not None:
+                r3, rB, rC, rN, rsb, rsc = _dense_view(residual)
+                if (rB, rC, rN) != (B, c_out, N):
+                    raise RuntimeError("dyn_conv_forward: residual must be (B, C_out, N, 1)")
+                fus.residual, fus.res_stride_b, fus.res_stride_c, fus.res_scale = _ptr(r3), rsb, rsc, float(res_scale)
+            if out is not None:
+                if tuple(out.shape[:3]) != (B, c_out, N) or out.dtype != torch.float32 or out.stride(2) != 1 or \
+                        out.stride(1) != N:
+                    raise RuntimeError("dyn_conv_forward: out must be a (B, C_out, N, 1) fp32 channel slice")
+                fus.out_stride_b = out.stride(0)
+        if out is None:
+            out = torch.empty((B, c_out, N, 1), dtype=torch.float32, device=dev)
         nbr = torch.empty((B, N, k), dtype=torch.int32, device=dev) if want_nbr else None
         ws = _workspace(l.dgcn_dyn_conv_workspace_bytes(CONV[conv], B, C, c_out, N, K), dev)
-        rc = l.dgcn_dyn_conv_forward(CONV[conv], _ptr(x3), B, C, N, sb, sc, ctypes.byref(dil), ctypes.byref(cs),
-                                     c_out, _ptr(out), _ptr(nbr), _ptr(ws), ws.numel(), _stream(dev))
+        rc = l.dgcn_dyn_conv_forward_fused(CONV[conv], _ptr(x3), B, C, N, sb, sc, ctypes.byref(dil), ctypes.byref(cs),
+                                           c_out, _ptr(out), _ptr(nbr), ctypes.byref(fus) if fus is not None else None,
+                                           _ptr(ws), ws.numel(), _stream(dev))
         _check(rc, "dgcn_dyn_conv_forward")
     return out, nbr
 

@@ -407,6 +407,7 @@ struct MrNodeArgs {
   float slope; const float* prelu;
   int norm; const float* bn_w; const float* bn_b; const float* bn_m; const float* bn_v; float bn_eps;
   float* out; float* partial;
+  const float* res; int64_t res_sb, res_sc; float res_scale; int64_t out_sb;   // block fusion (eval / no norm)
 };
 __global__ void __launch_bounds__(NTHREADS, 2) mr_node_kernel(const MrNodeArgs g) {
   __shared__ TileSmem ts;
@@ -437,7 +438,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) mr_node_kernel(const MrNodeArgs g
       const int n = n0 + tile_col(tx, j);
       float a = act_apply(acc[i][j] + bias, slope);
       if (m < g.co && n < g.N) {
-        g.out[(static_cast<int64_t>(b) * g.co + m) * g.N + n] = fmaf(s, a, t);
+        float v = fmaf(s, a, t);
+        if (g.res) v = __fadd_rn(v, __fmul_rn(__ldg(g.res + b * g.res_sb + m * g.res_sc + n), g.res_scale));
+        g.out[b * g.out_sb + static_cast<int64_t>(m) * g.N + n] = v;
         s1 += a;
         s2 += a * a;
       }
@@ -647,8 +650,12 @@ float act_slope_of(const dgcn_basic_conv* p) {
 static int conv_forward(int conv, const float* x, int64_t B, int64_t ci, int64_t N, int64_t sb, int64_t sc,
                         const int64_t* edge_index, const int32_t* nbr, int64_t k, const dgcn_dilation* dil,
                         const dgcn_basic_conv* p, int64_t co, float* out, int32_t* nbr_out, Workspace& ws,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const dgcn_block_fusion* fus = nullptr) {
   const bool fused = dil != nullptr;
+  if (fus) {   // block epilogue: out = conv + residual * scale, out possibly a channel slice of a wider buffer
+    if (!fused || p->norm == DGCN_NORM_BATCH_TRAIN) return DGCN_ERR_UNSUPPORTED;
+    if (fus->out_stride_b != 0 && fus->out_stride_b < co * N) return DGCN_ERR_BAD_ARG;
+  }
   const int64_t K = fused ? dil->k * dil->dilation : k;
   const int64_t keep = fused ? dil->k : k;
   ConvPlan pl = conv_plan(conv, B, ci, co, N, K, fused);
@@ -663,6 +670,10 @@ static int conv_forward(int conv, const float* x, int64_t B, int64_t ci, int64_t
   e.bn_w = p->bn_weight; e.bn_b = p->bn_bias; e.bn_m = p->bn_mean; e.bn_v = p->bn_var; e.bn_eps = p->bn_eps;
   e.c_out = static_cast<int>(co);
   e.c_in = static_cast<int>(ci);
+  e.out_sb = (fus && fus->out_stride_b) ? fus->out_stride_b : co * N;
+  if (fus && fus->residual && conv == DGCN_CONV_EDGE) {   // (MRConv adds it in its node kernel)
+    e.res = fus->residual; e.res_sb = fus->res_stride_b; e.res_sc = fus->res_stride_c; e.res_scale = fus->res_scale;
+  }
   float* wk = ws.take<float>(pl.wk);
   float* st = ws.take<float>(pl.st);
   float* partial = train ? ws.take<float>(pl.partial) : nullptr;
@@ -749,6 +760,10 @@ static int conv_forward(int conv, const float* x, int64_t B, int64_t ci, int64_t
   m.norm = p->norm; m.bn_w = p->bn_weight; m.bn_b = p->bn_bias; m.bn_m = p->bn_mean; m.bn_v = p->bn_var;
   m.bn_eps = p->bn_eps;
   m.out = out; m.partial = partial;
+  m.out_sb = e.out_sb;
+  if (fus && fus->residual) {
+    m.res = fus->residual; m.res_sb = fus->res_stride_b; m.res_sc = fus->res_stride_c; m.res_scale = fus->res_scale;
+  }
   mr_node_kernel<<<dim3(ceil_div(N, TILE), ceil_div(co, TILE), B), NTHREADS, 0, stream>>>(m);
   DGCN_LAUNCH_CHECK();
   if (train) {
@@ -810,12 +825,20 @@ size_t dgcn_dyn_conv_workspace_bytes(int32_t conv, int64_t B, int64_t C_in, int6
 int dgcn_dyn_conv_forward(int32_t conv, const float* x, int64_t B, int64_t C_in, int64_t N, int64_t stride_b,
                           int64_t stride_c, const dgcn_dilation* dil, const dgcn_basic_conv* p, int64_t C_out,
                           float* out, int32_t* nbr_out, void* wsp, size_t ws_bytes, dgcn_stream_t stream) {
+  return dgcn_dyn_conv_forward_fused(conv, x, B, C_in, N, stride_b, stride_c, dil, p, C_out, out, nbr_out, nullptr, wsp,
+                                     ws_bytes, stream);
+}
+
+int dgcn_dyn_conv_forward_fused(int32_t conv, const float* x, int64_t B, int64_t C_in, int64_t N, int64_t stride_b,
+                                int64_t stride_c, const dgcn_dilation* dil, const dgcn_basic_conv* p, int64_t C_out,
+                                float* out, int32_t* nbr_out, const dgcn_block_fusion* fus, void* wsp, size_t ws_bytes,
+                                dgcn_stream_t stream) {
   int rc = check_conv_args(conv, x, B, C_in, N, p, C_out, out);
   if (rc != DGCN_OK) return rc;
   if (!dil) return DGCN_ERR_BAD_ARG;
   Workspace ws(wsp, ws_bytes);
   return conv_forward(conv, x, B, C_in, N, stride_b, stride_c, nullptr, nullptr, 0, dil, p, C_out, out, nbr_out, ws,
-                      static_cast<cudaStream_t>(stream));
+                      static_cast<cudaStream_t>(stream), fus);
 }
 
 }  // extern "C"

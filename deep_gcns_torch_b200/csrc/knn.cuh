@@ -42,7 +42,17 @@ struct Epilogue {
   const float* xt;
   int c_in;
   float* r_out;
+  // block fusion (dgcn_block_fusion; eval / no norm only): out = conv + res * res_scale, written with batch
+  // stride out_sb (a channel slice of a wider buffer)
+  const float* res; int64_t res_sb, res_sc; float res_scale;
+  int64_t out_sb;        // batch stride of `out` in floats (c_out * N when out is contiguous)
 };
+
+// final value of output element (b, c, q): + skip connection.  Two roundings (x * scale, then the add) like the
+// reference's `self.body(x) + x * self.res_scale`.
+__device__ __forceinline__ float epi_res(const Epilogue& e, int b, int c, int q, float v) {
+  return e.res ? __fadd_rn(v, __fmul_rn(__ldg(e.res + b * e.res_sb + c * e.res_sc + q), e.res_scale)) : v;
+}
 
 struct KnnArgs {
   const float* x; int64_t sb, sc; int B, C, N; int vec;
@@ -248,11 +258,14 @@ __device__ __forceinline__ void cta_epilogue(const KnnArgs& a, int b, int q0, co
     }
     __syncthreads();
     float* dst = (e.mode == EPI_EDGE) ? e.out : e.r_out;
+    const int64_t dst_sb = (e.mode == EPI_EDGE) ? e.out_sb : static_cast<int64_t>(nch) * N;
     for (int i = tid; i < 32 * TILE; i += NW * 32) {
       const int cc = i >> 7, ql = i & (TILE - 1);
       if (c0 + cc < nch && q0 + ql < N && (ok == nullptr || ok[ql])) {
         int64_t o = (static_cast<int64_t>(b) * nch + c0 + cc) * N + q0 + ql;
-        dst[o] = stage_max[cc * STAGE_LD + ql];
+        float v = stage_max[cc * STAGE_LD + ql];
+        if (e.mode == EPI_EDGE && !train) v = epi_res(e, b, c0 + cc, q0 + ql, v);
+        dst[b * dst_sb + static_cast<int64_t>(c0 + cc) * N + q0 + ql] = v;
         if (train) e.out_min[o] = stage_min[cc * STAGE_LD + ql];
       }
     }
@@ -405,12 +418,18 @@ __device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q
         }
       }
     }
+    const int64_t dst_sb = edge ? e.out_sb : static_cast<int64_t>(nch) * N;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int64_t o = (static_cast<int64_t>(b) * nch + 4 * g + c) * N + q0 + qlb;
+      const int64_t o = (static_cast<int64_t>(b) * nch + 4 * g + c) * N + q0 + qlb;          // contiguous (out_min)
+      const int64_t oo = b * dst_sb + static_cast<int64_t>(4 * g + c) * N + q0 + qlb;        // out / r_out
+      if (edge && !TRAIN && e.res) {   // skip connection of the block: eight consecutive points of one channel
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res[i][c] = epi_res(e, b, 4 * g + c, q0 + qlb + i < N ? q0 + qlb + i : q0 + qlb, res[i][c]);
+      }
       if (all_live) {
-        *reinterpret_cast<float4*>(dst + o) = make_float4(res[0][c], res[1][c], res[2][c], res[3][c]);
-        *reinterpret_cast<float4*>(dst + o + 4) = make_float4(res[4][c], res[5][c], res[6][c], res[7][c]);
+        *reinterpret_cast<float4*>(dst + oo) = make_float4(res[0][c], res[1][c], res[2][c], res[3][c]);
+        *reinterpret_cast<float4*>(dst + oo + 4) = make_float4(res[4][c], res[5][c], res[6][c], res[7][c]);
         if (TRAIN) {
           *reinterpret_cast<float4*>(e.out_min + o) = make_float4(res2[0][c], res2[1][c], res2[2][c], res2[3][c]);
           *reinterpret_cast<float4*>(e.out_min + o + 4) =
@@ -421,7 +440,7 @@ __device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q
         for (int i = 0; i < 8; ++i) {
           const int ql = qlb + i;
           if (q0 + ql < N && ok[ql]) {
-            dst[o + i] = res[i][c];
+            dst[oo + i] = res[i][c];
             if (TRAIN) e.out_min[o + i] = res2[TRAIN ? i : 0][c];
           }
         }
@@ -680,14 +699,15 @@ __device__ __forceinline__ void row_consume(const KnnArgs& a, int b, int q, cons
       edge_query(e, node0, q, sel, k, c, slope, vmax, vmin, s1, s2);
       if (c < e.c_out) {
         int64_t o = (static_cast<int64_t>(b) * e.c_out + c) * N + q;
+        const int64_t oo = b * e.out_sb + static_cast<int64_t>(c) * N + q;
         if (train) {
-          e.out[o] = vmax;
+          e.out[oo] = vmax;
           e.out_min[o] = vmin;
           // one partial slot per query row: [row][2][c_out]
           e.partial[(static_cast<int64_t>(node0 + q) * 2 + 0) * e.c_out + c] = s1;
           e.partial[(static_cast<int64_t>(node0 + q) * 2 + 1) * e.c_out + c] = s2;
         } else {
-          e.out[o] = bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt);
+          e.out[oo] = epi_res(e, b, c, q, bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt));
         }
       }
     }

@@ -922,15 +922,16 @@ __global__ void __launch_bounds__(256) knn_exact_rows_kernel(const KnnArgs a, co
         edge_query(e, node0, q, sel, k, c, slope, vmax, vmin, s1, s2);
         if (c < e.c_out) {
           const int64_t o = (static_cast<int64_t>(b) * e.c_out + c) * N + q;
+          const int64_t oo = b * e.out_sb + static_cast<int64_t>(c) * N + q;
           if (train) {
-            e.out[o] = vmax;
+            e.out[oo] = vmax;
             e.out_min[o] = vmin;
             if (u < 4) {
               s1acc[u] += s1;
               s2acc[u] += s2;
             }
           } else {
-            e.out[o] = bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt);
+            e.out[oo] = epi_res(e, b, c, q, bs >= 0.f ? fmaf(bs, vmax, bt) : fmaf(bs, vmin, bt));
           }
         }
       }

@@ -23,8 +23,9 @@ class _GraphConvFn(torch.autograd.Function):
     def forward(ctx, owner, x, edge_index, fused, *params):
         prm = owner._conv_params()
         if fused is not None:                       # dynamic graph, built in the same launch sequence
-            k, dilation, cols, need_graph = fused
-            out, nbr = _native.dyn_conv_forward(owner._conv, x, prm, k, dilation, cols, want_nbr=need_graph)
+            k, dilation, cols, need_graph = fused[:4]
+            block = fused[4] if len(fused) > 4 else {}      # block epilogue (inference): residual / res_scale / out
+            out, nbr = _native.dyn_conv_forward(owner._conv, x, prm, k, dilation, cols, want_nbr=need_graph, **block)
         else:
             nbr = None
             out = _native.graph_conv_forward(owner._conv, x, prm, edge_index=edge_index)
@@ -88,15 +89,22 @@ class _DenseGraphConv(nn.Module):
             bn.running_mean.mul_(1 - mom).add_(prm.batch_mean, alpha=mom)
             bn.running_var.mul_(1 - mom).add_(unbiased, alpha=mom)
 
-    def _run(self, x, edge_index, fused=None):
+    def _run(self, x, edge_index, fused=None, block=None):
         conv, act, prelu, bn = self._parts()
         params = (conv.weight, conv.bias, prelu, None if bn is None else bn.weight, None if bn is None else bn.bias)
         if fused is not None:
             # the graph is kept (int32 neighbour list) only when a backward pass can follow
             need = torch.is_grad_enabled() and (x.requires_grad or any(
                 p is not None and p.requires_grad for p in params))
-            fused = tuple(fused) + (need,)
+            fused = tuple(fused) + (need,) + ((block,) if block else ())
         return _GraphConvFn.apply(self, x, edge_index, fused, *params)
+
+    def can_fuse_block(self, x):
+        """The block epilogue (skip connection / slice write in the consumer's store) runs without autograd and
+        without train-mode BatchNorm statistics."""
+        bn = self._parts()[3]
+        return (not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32 and
+                (bn is None or not (self.training or bn.running_mean is None)))
 
     def forward(self, x, edge_index):
         return self._run(x, edge_index)
@@ -141,14 +149,31 @@ class DynConv2d(GraphConv2d):
         else:
             self.dilated_knn_graph = DilatedKnnGraph(kernel_size, dilation, stochastic, epsilon)
 
-    def forward(self, x, edge_index=None):
-        if edge_index is not None:
-            return self.gconv(x, edge_index)
+    def forward(self, x, edge_index=None, residual=None, res_scale=1.0, out=None):
+        """`residual` / `res_scale` / `out` (beyond the reference's signature, used by the blocks below): fold the
+        block's skip connection and the write into a channel slice of a wider buffer into the consumer's store -
+        only on the fused dynamic path in inference; otherwise they are applied with plain torch ops."""
         g = self.dilated_knn_graph
-        if isinstance(g, DenseDilatedKnnGraph):
+        if edge_index is None and isinstance(g, DenseDilatedKnnGraph):
             # kNN selection and convolution in one call (dgcn_dyn_conv_forward)
-            return self.gconv._run(x, None, fused=(g.k, g.dilation, g.columns()))
-        return self.gconv(x, g(x))
+            block = None
+            if (residual is not None or out is not None) and self.gconv.can_fuse_block(x):
+                block = {}
+                if residual is not None:
+                    block.update(residual=residual, res_scale=res_scale)
+                if out is not None:
+                    block.update(out=out)
+            y = self.gconv._run(x, None, fused=(g.k, g.dilation, g.columns()), block=block)
+            if block is not None:
+                return y
+        else:
+            y = self.gconv(x, edge_index if edge_index is not None else g(x))
+        if residual is not None:
+            y = y + residual * res_scale
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
 
 
 class PlainDynBlock2d(nn.Module):
@@ -174,8 +199,10 @@ class ResDynBlock2d(nn.Module):
                               stochastic, epsilon, knn)
         self.res_scale = res_scale
 
-    def forward(self, x, edge_index=None):
-        return self.body(x, edge_index) + x * self.res_scale
+    def forward(self, x, edge_index=None, out=None):
+        """torch_vertex.py:101: body(x) + x * res_scale; the skip connection rides in the consumer's store in
+        inference.  `out` (optional, beyond the reference): a channel slice of the model's fusion buffer."""
+        return self.body(x, edge_index, residual=x, res_scale=self.res_scale, out=out)
 
 
 class DenseDynBlock2d(nn.Module):
@@ -188,4 +215,12 @@ class DenseDynBlock2d(nn.Module):
                               stochastic, epsilon, knn)
 
     def forward(self, x, edge_index=None):
+        """torch_vertex.py:116: cat((x, body(x)), 1); in inference the convolution writes its channel slice of the
+        result directly."""
+        if self.body.gconv.can_fuse_block(x) and edge_index is None:
+            c_in, c_out = x.shape[1], self.body.gconv.nn[0].out_channels
+            res = torch.empty((x.shape[0], c_in + c_out) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+            res[:, :c_in].copy_(x)
+            self.body(x, None, out=res[:, c_in:])
+            return res
         return torch.cat((x, self.body(x, edge_index)), 1)

@@ -147,6 +147,23 @@ int dgcn_dyn_conv_forward(int32_t conv, const float* x, int64_t B, int64_t C_in,
                           const dgcn_basic_conv* p, int64_t C_out, float* out, int32_t* nbr_out,
                           void* ws, size_t ws_bytes, dgcn_stream_t stream);
 
+/* Block epilogue around the dynamic convolution, inference (no train-mode BatchNorm):
+ *   residual != NULL: out = conv(x) + residual * res_scale   (ResDynBlock2d.forward, gcn_lib/dense/torch_vertex.py:101;
+ *     residual (B, C_out, N) with strides res_stride_b / res_stride_c, unit stride along points)
+ *   out_stride_b != 0: batch stride of `out` in floats - `out` is a channel slice of a wider (B, C_total, N) buffer
+ *     (DenseDynBlock2d's torch.cat, :116, or a model's fusion buffer, examples/sem_seg_dense/architecture.py:52). */
+typedef struct dgcn_block_fusion {
+  const float* residual;
+  int64_t res_stride_b, res_stride_c;
+  float res_scale;
+  int64_t out_stride_b;
+} dgcn_block_fusion;
+int dgcn_dyn_conv_forward_fused(int32_t conv, const float* x, int64_t B, int64_t C_in, int64_t N,
+                                int64_t stride_b, int64_t stride_c, const dgcn_dilation* dil,
+                                const dgcn_basic_conv* p, int64_t C_out, float* out, int32_t* nbr_out,
+                                const dgcn_block_fusion* fus /* may be NULL */, void* ws, size_t ws_bytes,
+                                dgcn_stream_t stream);
+
 /* Gradient of dgcn_graph_conv_forward w.r.t. x and the BasicConv parameters
  * (what torch autograd derives for torch_vertex.py:16-35 + torch_nn.py:48-58).
  * The graph is the one used in forward (edge_index (2,B,N,k) int64 or nbr

@@ -383,3 +383,48 @@ def test_tensor_core_prefilter_clustered_cloud_falls_back_exactly():
     finally:
         _native.set_knn_path("auto")
     assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("cfg", [
+    # C, N, k, d, conv, norm        (selection path)
+    (64, 512, 20, 1, "edge", "batch"),      # tensor-core path, wide consumer
+    (64, 512, 20, 4, "edge", "batch"),      # K = 80: slab path
+    (24, 100, 5, 2, "edge", None),          # fp32 small path, generic consumer
+    (32, 256, 9, 1, "mr", "batch"),         # MRConv: skip connection in the node kernel
+    (64, 384, 16, 3, "mr", "batch"),
+])
+def test_block_epilogues_fused_into_the_consumer(cfg):
+    """SURVEY.md 8f rank 1, dense: ResDynBlock2d's `+ x * res_scale` and the write into a channel slice of a wider
+    buffer (DenseDynBlock2d's cat, a model's fusion buffer) happen in the consumer's store in inference.  Must give
+    the bits of the unfused module sequence (conv, then x * scale, then the add)."""
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    C, N, k, d, conv, norm = cfg
+    g = torch.Generator().manual_seed(C + N)
+    torch.manual_seed(4)
+    x = torch.randn(3, C, N, 1, generator=g).cuda()
+    blk = D.ResDynBlock2d(C, k, d, conv, "relu", norm, True, res_scale=0.7).cuda().eval()
+    for m in blk.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data = torch.randn(C, generator=g).cuda()
+            m.running_mean.data = (torch.randn(C, generator=g) * 0.3).cuda()
+            m.running_var.data = (torch.rand(C, generator=g) + 0.4).cuda()
+    with torch.enable_grad():                       # autograd on: the reference's module sequence, nothing fused
+        ref = (blk.body(x) + x * blk.res_scale).detach()
+    with torch.no_grad():
+        got = blk(x)
+        wide = torch.full((3, 3 * C, N, 1), float("nan"), device="cuda")
+        wide[:, :C] = x
+        ret = blk(wide[:, :C], out=wide[:, 2 * C:])            # strided input slice, strided output slice
+    assert torch.equal(got, ref)
+    assert ret.data_ptr() == wide[:, 2 * C:].data_ptr() and torch.equal(wide[:, 2 * C:], ref)
+    assert torch.isnan(wide[:, C:2 * C]).all()                  # nothing outside the slice was touched
+    dense_blk = D.DenseDynBlock2d(C, 32, k, d, conv, "relu", norm, True).cuda().eval()
+    with torch.enable_grad():
+        ref_cat = torch.cat((x, dense_blk.body(x)), 1).detach()
+    with torch.no_grad():
+        assert torch.equal(dense_blk(x), ref_cat)
+    blk.train()                                     # train-mode BatchNorm: falls back to the module sequence
+    if norm == "batch":
+        with torch.no_grad():
+            y_train = blk(x)
+        assert y_train.shape == ref.shape and torch.isfinite(y_train).all()

@@ -40,6 +40,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_native.GenconvParamsC) == 80
     assert ctypes.sizeof(_native.CsrHubsC) == 40
     assert ctypes.sizeof(_native.GenconvFusionC) == 40
+    assert ctypes.sizeof(_native.BlockFusionC) == 40
 
 
 def test_no_cpu_fallback():
