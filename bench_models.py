@@ -169,9 +169,10 @@ def main():
             ms_bb = timeit(lambda: model.backbone_forward(inputs))
             ms_bb_fused = timeit(lambda: model.backbone_forward_fused(inputs))
             torch.manual_seed(3)
-            a = torch.cat(model.backbone_forward(inputs), 1)
+            unfused = torch.cat(model.backbone_forward(inputs), 1)
             torch.manual_seed(3)
-            assert torch.equal(a, model.backbone_forward_fused(inputs))      # same bits, two passes fewer per block
+            assert torch.equal(unfused, model.backbone_forward_fused(inputs))      # same bits, two passes fewer per block
+            del unfused
             ms_all = timeit(lambda: model(inputs))
             per_layer = []
             feats = model.head(inputs, model.knn(inputs[:, 0:3]))

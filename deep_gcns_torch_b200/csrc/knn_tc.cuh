@@ -468,6 +468,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const __grid_cons
   unsigned char* stage = work + TC_STAGE_BYTES;
 
   if (tid == 0) {
+    // the TMA descriptors live in kernel-parameter space: fetch them into the descriptor cache before the first load
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&t.tm_planes)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&t.tm_sqp)) : "memory");
     mbar_init(&sm.mbar, 1);
     mbar_init(&sm.mbar_drained, TC_THREADS);
     mbar_init(&sm.mbar_tma, 1);
