@@ -142,5 +142,38 @@ def main():
          {"x": x, "edge_index": ei.to(torch.int32), "edge_attr": ea}, coupling.state_dict(), {"y": y, "x_back": x_back})
 
 
+def sparse_layout_convs():
+    """gcn_lib/sparse/torch_vertex.py:91-103, 267-312: MRConv on a random graph (isolated nodes, duplicates) for every
+    aggregator, and a ResDynBlock('mr') over equally sized clouds (dilated kNN graph by pairwise distance)."""
+    ref_shims.load_reference()
+    tv = sys.modules["gcn_lib.sparse.torch_vertex"]
+    gen = torch.Generator().manual_seed(21)
+    N, E, C = 240, 2000, 24
+    ei = torch.stack((torch.randint(0, N - 15, (E,), generator=gen), torch.randint(0, N - 9, (E,), generator=gen)))
+    x = torch.randn(N, C, generator=gen)
+    outs, sds = {}, {}
+    for aggr in ("max", "add", "mean", "min"):
+        torch.manual_seed(5)
+        conv = tv.MRConv(C, 32, "relu", "batch", True, aggr).eval()
+        randomize_norm(conv, gen)
+        with torch.no_grad():
+            outs["y_" + aggr] = conv(x, ei)
+        sds.update({aggr + "." + k: v for k, v in conv.state_dict().items()})
+    B, n = 3, 80
+    xb = torch.randn(B * n, C, generator=gen)
+    batch = torch.arange(B).repeat_interleave(n)
+    torch.manual_seed(6)
+    blk = tv.ResDynBlock(C, 6, 2, "mr", "relu", "batch", True, res_scale=0.5).eval()
+    randomize_norm(blk, gen)
+    with torch.no_grad():
+        yb, _ = blk(xb, batch)
+        eib = blk.body.dilated_knn_graph(xb, batch)
+    outs["y_block"], outs["edge_index_block"] = yb, eib.to(torch.int32)
+    sds.update({"block." + k: v for k, v in blk.state_dict().items()})
+    save("spconv_mr", dict(N=N, C=C, out=32, B=B, n=n, k=6, dilation=2, res_scale=0.5),
+         {"x": x, "edge_index": ei.to(torch.int32), "xb": xb, "batch": batch.to(torch.int32)}, sds, outs)
+
+
 if __name__ == "__main__":
     main()
+    sparse_layout_convs()

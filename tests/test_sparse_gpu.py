@@ -270,3 +270,45 @@ def test_tcgen05_row_linear_with_bias_and_skip(N, K, M):
     torch.testing.assert_close(buf, (a.double() @ w.double().t() + b.double() + h.double()).float(), rtol=1e-3, atol=1e-4)
     assert not _native.linear_residual_supported(100, 128) and not _native.linear_residual_supported(128, 300)
     assert not _native.linear_residual_supported(256, 256)            # operands would not fit one SM's shared memory
+
+
+def test_sparse_layout_mrconv_and_dyn_block_match_reference():
+    """gcn_lib/sparse/torch_vertex.py:91-103 (MRConv, all aggregators, isolated nodes) and :300-312 (ResDynBlock
+    over equally sized clouds) against the unmodified reference (golden spconv_mr), forward and backward."""
+    from deep_gcns_torch_b200.gcn_lib import sparse as S
+    c = gu.load("spconv_mr")
+    m = c.meta
+    x, ei = c.ins["x"].cuda(), c.ins["edge_index"].long().cuda()
+    for aggr in ("max", "add", "mean", "min"):
+        conv = S.MRConv(m["C"], m["out"], "relu", "batch", True, aggr)
+        conv.load_state_dict({k[len(aggr) + 1:]: v for k, v in c.sd.items() if k.startswith(aggr + ".")}, strict=True)
+        conv = conv.cuda().eval()
+        with torch.no_grad():
+            y = conv(x, ei)
+        torch.testing.assert_close(y.cpu(), c.outs["y_" + aggr], rtol=RTOL, atol=ATOL, msg=lambda s_, a=aggr: a + ": " + s_)
+    blk = S.ResDynBlock(m["C"], m["k"], m["dilation"], "mr", "relu", "batch", True, res_scale=m["res_scale"])
+    blk.load_state_dict({k[6:]: v for k, v in c.sd.items() if k.startswith("block.")}, strict=True)
+    blk = blk.cuda().eval()
+    xb, batch = c.ins["xb"].cuda(), c.ins["batch"].long().cuda()
+    with torch.no_grad():
+        yb, b2 = blk(xb, batch)
+        eib = blk.body.dilated_knn_graph(xb, batch)
+    assert b2 is batch
+    same = (eib.cpu().view(2, -1, m["k"])[0].sort(-1).values ==
+            c.outs["edge_index_block"].long().view(2, -1, m["k"])[0].sort(-1).values).all(-1)
+    assert same.float().mean() > 0.99
+    torch.testing.assert_close(yb.cpu()[same], c.outs["y_block"][same], rtol=RTOL, atol=ATOL)
+    # gradients flow through the raw max aggregation (arg-max routing) like torch_scatter's scatter_max
+    conv = S.MRConv(m["C"], m["out"], "relu", None, True, "max").cuda()
+    xg = x.clone().requires_grad_(True)
+    conv(xg, ei).sum().backward()
+    xr = x.detach().cpu().double().requires_grad_(True)
+    src, dst = ei.cpu()
+    msg = xr[src] - xr[dst]
+    agg = torch.zeros(m["N"], m["C"], dtype=torch.double).scatter_reduce(0, dst.view(-1, 1).expand(-1, m["C"]), msg, "amax",
+                                                                         include_self=False)
+    lin = conv.nn[0]
+    torch.relu(torch.cat([xr, agg], 1) @ lin.weight.detach().cpu().double().t() + lin.bias.detach().cpu().double()).sum().backward()
+    torch.testing.assert_close(xg.grad.cpu().double(), xr.grad, rtol=1e-3, atol=1e-4)
+    with pytest.raises(NotImplementedError):
+        S.GraphConv(8, 8, "gat")
