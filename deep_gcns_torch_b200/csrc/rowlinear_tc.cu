@@ -13,12 +13,13 @@
 // TMEM: error <= ~2^-16 sum_k |a||W| (1.5e-5 relative to the magnitude sum), two orders below the 1e-3 parity
 // tolerance.  W is split once per call by a prep kernel; a is split on the fly by the producer warps.
 //
-// One persistent CTA per SM, 256 threads:
-//   warps 4-7 (producers)  tile of 128 rows: coalesced 256-bit loads of a -> (hi, mid) bf16 -> shared memory in the
+// One persistent CTA per SM, 384 threads:
+//   warps 8-11 (producers)  tile of 128 rows: coalesced 256-bit loads of a -> (hi, mid) bf16 -> shared memory in the
 //                          canonical K-major SWIZZLE_128B UMMA layout [plane][K/64][128 rows][128 B]; the first
 //                          producer thread then issues the 4 x K/16 tcgen05.mma (M=128, N=M_out, K=16) into one of
 //                          two TMEM accumulators and commits.
-//   warps 0-3 (epilogue)   previous tile: tcgen05.ld (thread = row, 32 columns), transpose through a padded
+//   warps 0-7 (epilogue)   previous tile, two warps per TMEM lane quarter taking alternate 32-column blocks (twice the
+//                          skip-connection loads in flight): tcgen05.ld (thread = row, 32 columns), transpose through a padded
 //                          shared-memory stage, then row-contiguous out = acc + bias + res.
 //   W (hi, mid)            resident in shared memory for the life of the CTA, loaded once by TMA.
 #include <cuda.h>
@@ -127,11 +128,13 @@ struct RlBars {
   uint64_t w_full;          // W planes landed
   uint64_t a_full;          // all 128 producer threads wrote (and fenced) their part of the A tile
   uint64_t mma_done[2];     // MMAs of the tile in accumulator i have completed (A free, accumulator readable)
-  uint64_t acc_free[2];     // the 128 epilogue threads have drained accumulator i
+  uint64_t acc_free[2];     // the 256 epilogue threads have drained accumulator i
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(256, 1) rowlinear_tc_kernel(const __grid_constant__ RlArgs g) {
+constexpr int RL_EPI_THREADS = 256;   // warps 0..7
+
+__global__ void __launch_bounds__(RL_EPI_THREADS + 128, 1) rowlinear_tc_kernel(const __grid_constant__ RlArgs g) {
   extern __shared__ __align__(16) unsigned char rl_smem[];
   unsigned char* base = rl_smem + ((1024u - (rl_smem_u32(rl_smem) & 1023u)) & 1023u);
   const int K = g.K, M = g.M;
@@ -140,8 +143,8 @@ __global__ void __launch_bounds__(256, 1) rowlinear_tc_kernel(const __grid_const
   const uint32_t a_plane = static_cast<uint32_t>(RL_TILE) * K * 2;
   unsigned char* w_s = base;                                            // [2][kblocks][M][128 B]
   unsigned char* a_s = w_s + 2 * w_plane;                               // [2][kblocks][128][128 B]
-  float* stage = reinterpret_cast<float*>(a_s + 2 * a_plane);           // [4 warps][32][33]
-  RlBars& bar = *reinterpret_cast<RlBars*>(reinterpret_cast<unsigned char*>(stage) + 4 * 32 * 33 * 4);
+  float* stage = reinterpret_cast<float*>(a_s + 2 * a_plane);           // [8 warps][32][33]
+  RlBars& bar = *reinterpret_cast<RlBars*>(reinterpret_cast<unsigned char*>(stage) + 8 * 32 * 33 * 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (g.N + RL_TILE - 1) / RL_TILE;
 
@@ -150,8 +153,8 @@ __global__ void __launch_bounds__(256, 1) rowlinear_tc_kernel(const __grid_const
     rl_mbar_init(&bar.a_full, 128);
     rl_mbar_init(&bar.mma_done[0], 1);
     rl_mbar_init(&bar.mma_done[1], 1);
-    rl_mbar_init(&bar.acc_free[0], 128);
-    rl_mbar_init(&bar.acc_free[1], 128);
+    rl_mbar_init(&bar.acc_free[0], RL_EPI_THREADS);
+    rl_mbar_init(&bar.acc_free[1], RL_EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -165,9 +168,9 @@ __global__ void __launch_bounds__(256, 1) rowlinear_tc_kernel(const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = bar.tmem_base;
 
-  if (warp >= 4) {
+  if (warp >= RL_EPI_THREADS / 32) {
     // ======================= producers (+ MMA issue by their first thread) ===========================================
-    const int pt = tid - 128;
+    const int pt = tid - RL_EPI_THREADS;
     if (pt == 0) {   // W: one box of 64 k x M rows per (plane, k-block)
       rl_mbar_expect_tx(&bar.w_full, 2 * w_plane);
       for (int pl = 0; pl < 2; ++pl)
@@ -247,26 +250,28 @@ __global__ void __launch_bounds__(256, 1) rowlinear_tc_kernel(const __grid_const
   } else {
     // ======================= epilogue: out = acc + bias + res ========================================================
     float* st = stage + warp * 32 * 33;
+    const int quarter = warp & 3, half = warp >> 2;      // TMEM lane quarter; which of the alternating column blocks
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int acc = static_cast<int>(it & 1);
       rl_mbar_wait(&bar.mma_done[acc], static_cast<uint32_t>((it >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t row0 = tile * RL_TILE + warp * 32;
+      const int64_t row0 = tile * RL_TILE + quarter * 32;
       // lane = column.  The 32 rows' skip-connection values of a 32-column block are loaded one block ahead: 32
       // independent 128-byte row segments per warp stay in flight while the previous block is read from TMEM,
       // transposed through the padded stage and stored.
       float rv[32], rn[32];
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) rv[rr] = (g.res && row0 + rr < g.N) ? __ldg(g.res + (row0 + rr) * M + lane) : 0.f;
-      for (int cb = 0; cb < M; cb += 32) {
-        const bool more = cb + 32 < M;
+      for (int rr = 0; rr < 32; ++rr)
+        rv[rr] = (g.res && half * 32 < M && row0 + rr < g.N) ? __ldg(g.res + (row0 + rr) * M + half * 32 + lane) : 0.f;
+      for (int cb = half * 32; cb < M; cb += 64) {
+        const bool more = cb + 64 < M;
 #pragma unroll
         for (int rr = 0; rr < 32; ++rr)
-          rn[rr] = (more && g.res && row0 + rr < g.N) ? __ldg(g.res + (row0 + rr) * M + cb + 32 + lane) : 0.f;
+          rn[rr] = (more && g.res && row0 + rr < g.N) ? __ldg(g.res + (row0 + rr) * M + cb + 64 + lane) : 0.f;
         uint32_t v[32];
         __syncwarp();
-        rl_tmem_ld32(tmem + static_cast<uint32_t>(acc * M + cb) + (static_cast<uint32_t>(warp * 32) << 16), v);
+        rl_tmem_ld32(tmem + static_cast<uint32_t>(acc * M + cb) + (static_cast<uint32_t>(quarter * 32) << 16), v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
         __syncwarp();
@@ -307,7 +312,7 @@ static RlEncodeFn rl_encoder() {
 }
 
 static size_t rl_smem_bytes(int64_t K, int64_t M) {
-  return static_cast<size_t>(2) * M * K * 2 + static_cast<size_t>(2) * RL_TILE * K * 2 + 4 * 32 * 33 * 4 + sizeof(RlBars) + 1024;
+  return static_cast<size_t>(2) * M * K * 2 + static_cast<size_t>(2) * RL_TILE * K * 2 + 8 * 32 * 33 * 4 + sizeof(RlBars) + 1024;
 }
 static bool rl_shape_ok(int64_t K, int64_t M) {
   // 128 | rows per pass = 1024 / K; W planes + A planes + stage must fit the 227 KB of one SM
@@ -362,7 +367,7 @@ int dgcn_linear_residual(const float* a, int64_t N, int64_t K, const float* weig
   const unsigned grid = static_cast<unsigned>(ntiles < sms ? ntiles : sms);
   {
     KernelTimer timer(stream, "linear");
-    rowlinear_tc_kernel<<<grid, 256, smem, stream>>>(g);
+    rowlinear_tc_kernel<<<grid, RL_EPI_THREADS + 128, smem, stream>>>(g);
   }
   DGCN_LAUNCH_CHECK();
   return DGCN_OK;

@@ -28,7 +28,14 @@ __all__ = ["bn_eval_affine", "res_plus_block", "res_plus_block_partitioned", "fu
 
 
 def bn_eval_affine(norm):
-    """(scale, shift) with norm(h) = scale * h + shift for an eval-mode BatchNorm1d (running statistics)."""
+    """(scale, shift) with norm(h) = scale * h + shift for an eval-mode BatchNorm1d (running statistics).
+    Cached on the module (a plain attribute, not a buffer: nothing new in state_dict) until one of the four
+    tensors it derives from changes (tensor version counters / identity)."""
+    src = (norm.running_var, norm.running_mean, norm.weight, norm.bias)
+    key = tuple((id(t), t._version, t.device) if t is not None else None for t in src) + (norm.eps,)
+    hit = norm.__dict__.get("_dgcn_eval_affine")
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
     var, mean = norm.running_var, norm.running_mean
     scale = torch.rsqrt(var + norm.eps)
     if norm.weight is not None:
@@ -36,6 +43,8 @@ def bn_eval_affine(norm):
     shift = -mean * scale
     if norm.bias is not None:
         shift = shift + norm.bias
+    scale, shift = scale.detach().contiguous(), shift.detach().contiguous()
+    norm.__dict__["_dgcn_eval_affine"] = (key, scale, shift)
     return scale, shift
 
 
