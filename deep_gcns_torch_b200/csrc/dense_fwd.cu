@@ -9,6 +9,13 @@
 
 namespace dgcn {
 
+// tensor-core distance rows of the large-K slab path (dist_rows_tc.cu)
+bool dist_rows_tc_ok(const KnnArgs& a);
+size_t dist_rows_tc_plane_elems(int64_t B, int64_t C, int64_t N);
+int dist_rows_tc_prepare(const KnnArgs& a, __nv_bfloat16* planes, cudaStream_t stream);
+int dist_rows_tc_launch(const KnnArgs& a, const __nv_bfloat16* planes, int b0, int nb, float* drows, int ldd,
+                        cudaStream_t stream);
+
 __global__ void to_node_major_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C, int N,
                                      float* __restrict__ xt);
 
@@ -43,6 +50,7 @@ size_t knn_workspace_bytes(int64_t B, int64_t C, int64_t N, int64_t K) {
     const size_t nslab = static_cast<size_t>(B) > knn_slab_clouds(B, N) ? 2 : 1;   // two slabs: distance rows of slab s+1 overlap the select of slab s
     bytes += nslab * align_up(knn_slab_clouds(B, N) * N * ldd * 4, 256);
     bytes += align_up(knn_slab_clouds(B, N) * N * 4 + 256, 256);   // rows the sampled select hands to the exact kernel
+    if (C <= TC_MAX_C && N >= TILE && N % TILE == 0) bytes += align_up(dist_rows_tc_plane_elems(B, C, N) * 2, 256);   // (hi, mid, lo) planes
   }
   return bytes + 256;
 }
@@ -199,8 +207,17 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
   if (knn_takes_tc(a))
     return launch_knn_tc(a, ws, stream, a.epi.mode == EPI_MR ? a.epi.xt : nullptr, n_partial, pqf);
   if (pqf) return DGCN_ERR_BAD_ARG;   // (internal misuse) nobody would produce PQ
-  sqnorm_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(a.x, a.sb, a.sc, a.C, N, sq);
-  DGCN_LAUNCH_CHECK();
+  const bool rows_on_tc = K > 32 && K <= LARGE_K_MAX && dist_rows_tc_ok(a);   // large-K: distance rows on tcgen05
+  __nv_bfloat16* planes3 = nullptr;
+  if (rows_on_tc) {
+    planes3 = ws.take<__nv_bfloat16>(dist_rows_tc_plane_elems(B, a.C, N));
+    if (!ws.ok) return DGCN_ERR_WORKSPACE;
+    int rc = dist_rows_tc_prepare(a, planes3, stream);      // sq (same FMA chain as sqnorm_kernel) + the bf16 planes
+    if (rc != DGCN_OK) return rc;
+  } else {
+    sqnorm_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, stream>>>(a.x, a.sb, a.sc, a.C, N, sq);
+    DGCN_LAUNCH_CHECK();
+  }
   const dim3 grid(ceil_div(N, TILE), B);
   if (n_partial) *n_partial = K <= SMALL_K_MAX ? static_cast<int64_t>(grid.x) * grid.y : static_cast<int64_t>(B) * N;
   if (K <= 32) {
@@ -280,10 +297,18 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
     float* drows_s = buf ? drows2 : drows;
     if (side) {
       if (slab >= 2) DGCN_CUDA_TRY(cudaStreamWaitEvent(side, ev_sel[buf], 0));   // the select two slabs back has left this buffer
-      dist_rows_kernel<<<dim3(ceil_div(N, TILE), ceil_div(N, TILE), nb), NTHREADS, 0, side>>>(a, b0, drows_s, ldd);
-      DGCN_LAUNCH_CHECK();
+      if (rows_on_tc) {
+        int rc = dist_rows_tc_launch(a, planes3, b0, nb, drows_s, ldd, side);
+        if (rc != DGCN_OK) return rc;
+      } else {
+        dist_rows_kernel<<<dim3(ceil_div(N, TILE), ceil_div(N, TILE), nb), NTHREADS, 0, side>>>(a, b0, drows_s, ldd);
+        DGCN_LAUNCH_CHECK();
+      }
       DGCN_CUDA_TRY(cudaEventRecord(ev_dist[buf], side));
       DGCN_CUDA_TRY(cudaStreamWaitEvent(stream, ev_dist[buf], 0));
+    } else if (rows_on_tc) {
+      int rc = dist_rows_tc_launch(a, planes3, b0, nb, drows_s, ldd, stream);
+      if (rc != DGCN_OK) return rc;
     } else {
       dist_rows_kernel<<<dim3(ceil_div(N, TILE), ceil_div(N, TILE), nb), NTHREADS, 0, stream>>>(a, b0, drows_s, ldd);
       DGCN_LAUNCH_CHECK();
