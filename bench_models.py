@@ -142,6 +142,28 @@ class DeeperGCN(torch.nn.Module):
         return torch.log_softmax(self.pred(F.relu(self.norms[L - 1](h))), dim=-1)
 
 
+def graph_timeit(fn, steps=5):
+    """The same call captured once into a CUDA graph (launch gaps between the model's kernels disappear) and
+    replayed: ms per replay, and the captured output for a parity check."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fn()                                   # warm-up on the capture stream: caches, allocator pools
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = fn()
+    graph.replay()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        graph.replay()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps * 1e3, out
+
+
 def timeit(fn, steps=5):
     fn()
     torch.cuda.synchronize()
@@ -174,13 +196,19 @@ def main():
             assert torch.equal(unfused, model.backbone_forward_fused(inputs))      # same bits, two passes fewer per block
             del unfused
             ms_all = timeit(lambda: model(inputs))
+            try:
+                torch.manual_seed(3)
+                ms_graph, g_out = graph_timeit(lambda: model.backbone_forward_fused(inputs))
+            except Exception as exc:
+                ms_graph = "failed: %s: %s" % (type(exc).__name__, str(exc)[:200])
             per_layer = []
             feats = model.head(inputs, model.knn(inputs[:, 0:3]))
             for i in (0, 1, 2, 3, 7, 15, 26):
                 blk = model.backbone[i]
                 per_layer.append({"dilation": i + 1, "K": 20 * (i + 1), "ms": timeit(lambda: blk(feats), 3)})
         edges = 28 * 16 * 4096 * 20
-        out["c2_resgcn28"] = {"backbone_ms": ms_bb, "backbone_ms_fused_blocks": ms_bb_fused, "model_ms": ms_all, "edges_per_s_backbone": edges / (ms_bb * 1e-3),
+        out["c2_resgcn28"] = {"backbone_ms": ms_bb, "backbone_ms_fused_blocks": ms_bb_fused,
+                              "backbone_ms_fused_blocks_cuda_graph": ms_graph, "model_ms": ms_all, "edges_per_s_backbone": edges / (ms_bb * 1e-3),
                               "per_layer": per_layer}
     if "c4" in a.which:      # per-GPU share of config 4 (B=64 over 8 GPUs): forward + backward + SGD step
         torch.manual_seed(0)
@@ -212,8 +240,15 @@ def main():
         with torch.no_grad():
             ms = timeit(lambda: model(x, ei))
             ms_fused = timeit(lambda: model.forward_fused(x, ei))
-            torch.testing.assert_close(model.forward_fused(x, ei), model(x, ei), rtol=1e-3, atol=1e-4)
+            ref_out = model(x, ei)
+            torch.testing.assert_close(model.forward_fused(x, ei), ref_out, rtol=1e-3, atol=1e-4)
+            try:
+                ms_graph, g_out = graph_timeit(lambda: model.forward_fused(x, ei))
+                torch.testing.assert_close(g_out, ref_out, rtol=1e-3, atol=1e-4)
+            except Exception as exc:                       # report, do not hide
+                ms_graph = "failed: %s: %s" % (type(exc).__name__, str(exc)[:200])
         out["c3_deepergcn56"] = {"model_ms": ms, "model_ms_fused_blocks": ms_fused,
+                                 "model_ms_fused_blocks_cuda_graph": ms_graph,
                                  "edges_per_s": 56 * ei.shape[1] / (ms_fused * 1e-3), "E": int(ei.shape[1])}
     print(json.dumps(out))
 

@@ -43,8 +43,8 @@ def csr_of(edge_index, num_nodes, cache=True):
         if hit is not None:
             _csr_cache.move_to_end(key)
             _, csr, stream_id, done = hit
-            if cur is not None and stream_id != cur.cuda_stream:
-                cur.wait_event(done)
+            if cur is not None and stream_id != cur.cuda_stream and not done.query():
+                cur.wait_event(done)          # (a build that has already finished needs no edge: keeps graph capture legal)
             return csr
     csr = _native.csr_build(edge_index, int(num_nodes))
     done, stream_id = None, None
