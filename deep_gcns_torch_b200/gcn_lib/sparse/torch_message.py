@@ -43,8 +43,15 @@ def csr_of(edge_index, num_nodes, cache=True):
         if hit is not None:
             _csr_cache.move_to_end(key)
             _, csr, stream_id, done = hit
-            if cur is not None and stream_id != cur.cuda_stream and not done.query():
-                cur.wait_event(done)          # (a build that has already finished needs no edge: keeps graph capture legal)
+            if cur is not None and stream_id is not None and stream_id != cur.cuda_stream:
+                # first use from another stream: the build must be complete before this stream reads it.  Settle it
+                # once on the host (afterwards the entry is valid for every stream, including a graph-capture stream,
+                # where neither an event wait on uncaptured work nor an event query is legal).
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("csr_of: this graph's CSR was built on another stream and has not been used from "
+                                       "a second stream yet - run one warm-up forward before CUDA-graph capture")
+                done.synchronize()
+                hit[2] = None
             return csr
     csr = _native.csr_build(edge_index, int(num_nodes))
     done, stream_id = None, None
@@ -53,7 +60,7 @@ def csr_of(edge_index, num_nodes, cache=True):
         done.record(cur)
         stream_id = cur.cuda_stream
     with _csr_lock:
-        _csr_cache[key] = (edge_index, csr, stream_id, done)
+        _csr_cache[key] = [edge_index, csr, stream_id, done]
         while len(_csr_cache) > CSR_CACHE_SIZE:
             _csr_cache.popitem(last=False)
     return csr
