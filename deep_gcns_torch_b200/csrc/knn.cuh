@@ -852,6 +852,10 @@ __global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const f
     if (a.exclude_self && i == q) key = 0xFFFFFFFFu;
     sk[s] = static_cast<uint64_t>(key);
   }
+  // the first 128 distances of the row: in flight under the sample sort
+  float first[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) first[u] = (u * 32 + lane < N) ? __ldg(drow + u * 32 + lane) : 0.f;
   __syncwarp();
   warp_bitonic_sort(sk, 128, lane);
   // keep the sorted sample in registers: lane l holds samples l, l+32, l+64, l+96
@@ -859,22 +863,33 @@ __global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const f
 #pragma unroll
   for (int u = 0; u < 4; ++u) smp[u] = static_cast<uint32_t>(sk[lane + 32 * u]);
   __syncwarp();
-  // 2. compaction in index order of every key <= bound; if the sample misjudged the row (too few or too
-  //    many keys below the bound) move the bound along the sorted sample and try again
+  // 2. compaction in index order of every distance <= bound; if the sample misjudged the row (too few or too
+  //    many below the bound) move the bound along the sorted sample and try again.  The pass is the bulk of
+  //    this kernel's instructions, so it works on the raw floats: one FSETP against the bound (a float compare
+  //    admits the same set as the ordered-key compare except that -0 and +0 tie, which only widens the superset;
+  //    NaN never passes), the entry is stored as (float bits, index) and converted to an ordered key afterwards,
+  //    for the ~K..2K survivors only.
+  const int q_self = a.exclude_self ? q : -1;
   int w = 0, rank = sample_rank, lo_rank = -1, hi_rank = 128;   // lo_rank: too few, hi_rank: too many
   bool ok = false;
+  const bool full_groups = (N & 127) == 0;
   for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
     uint32_t bound = __shfl_sync(0xffffffffu, smp[0], rank & 31);
     if ((rank >> 5) == 1) bound = __shfl_sync(0xffffffffu, smp[1], rank & 31);
     if ((rank >> 5) == 2) bound = __shfl_sync(0xffffffffu, smp[2], rank & 31);
     if ((rank >> 5) == 3) bound = __shfl_sync(0xffffffffu, smp[3], rank & 31);
+    const float bound_f = ordered_to_float(bound);
+    const unsigned lt_mask = (1u << lane) - 1u;
     w = 0;
     float nxt[4];                        // the next 128 distances are in flight while these are compacted
+    if (attempt == 0) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) nxt[u] = (u * 32 + lane < N) ? __ldg(drow + u * 32 + lane) : 0.f;
+      for (int u = 0; u < 4; ++u) nxt[u] = first[u];             // issued before the sample sort
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nxt[u] = (u * 32 + lane < N) ? __ldg(drow + u * 32 + lane) : 0.f;
+    }
     for (int i0 = 0; i0 < N; i0 += 128) {
-      uint32_t key[4];
-      bool take[4];
       float cur[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
@@ -886,15 +901,11 @@ __global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const f
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + u * 32 + lane;
-        key[u] = 0xFFFFFFFFu;
-        if (i < N) key[u] = float_to_ordered(cur[u]);
-        take[u] = (i < N) && key[u] <= bound && !(a.exclude_self && i == q);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const unsigned m = __ballot_sync(0xffffffffu, take[u]);
-        const int pos = w + __popc(m & ((1u << lane) - 1u));
-        if (take[u] && pos < CAP) sk[pos] = (static_cast<uint64_t>(key[u]) << 32) | static_cast<uint32_t>(i0 + u * 32 + lane);
+        bool take = cur[u] <= bound_f && i != q_self;
+        if (!full_groups) take = take && i < N;
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        const int pos = w + __popc(m & lt_mask);
+        if (take && pos < CAP) sk[pos] = (static_cast<uint64_t>(__float_as_uint(cur[u])) << 32) | static_cast<uint32_t>(i);
         w += __popc(m);
       }
     }
@@ -909,6 +920,14 @@ __global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const f
       if (rank <= lo_rank) break;
     } else {
       ok = true;
+    }
+    __syncwarp();
+  }
+  if (ok) {   // raw float bits -> ordered keys (the survivors are never NaN: the compare rejects it)
+    for (int i = lane; i < w; i += 32) {
+      const uint64_t e = sk[i];
+      sk[i] = (static_cast<uint64_t>(float_to_ordered(__uint_as_float(static_cast<uint32_t>(e >> 32)))) << 32) |
+              static_cast<uint32_t>(e);
     }
     __syncwarp();
   }
