@@ -38,6 +38,7 @@ class DilationC(ctypes.Structure):
 
 
 KNN_EXACT_FP32 = 1         # dgcn_knn_flags
+KNN_TC_TILE_PER_CTA = 2
 _knn_flags = threading.local()
 
 
@@ -543,6 +544,8 @@ def kernel_timing_read(tag):
 
 def set_knn_path(path):
     """A/B switch for tests and measurements: 'ffma' makes the calls of THIS thread pass
-    DGCN_KNN_EXACT_FP32 (fp32 FMA selection kernels only); 'tc' / 'auto' = the default routing
-    (tcgen05 pre-filter + exact re-rank where the shape allows).  The library holds no state."""
-    _knn_flags.value = {"ffma": KNN_EXACT_FP32, "tc": 0, "auto": 0}[path]
+    DGCN_KNN_EXACT_FP32 (fp32 FMA selection kernels only); 'tc1' passes DGCN_KNN_TC_TILE_PER_CTA (tensor-core
+    pre-filter, always the one-tile-per-CTA kernel); 'tc' / 'auto' = the default routing (tcgen05 pre-filter +
+    exact re-rank where the shape allows, four query tiles per CTA where that kernel applies).  The library
+    holds no state."""
+    _knn_flags.value = {"ffma": KNN_EXACT_FP32, "tc1": KNN_TC_TILE_PER_CTA, "tc": 0, "auto": 0}[path]

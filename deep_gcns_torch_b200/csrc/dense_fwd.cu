@@ -5,7 +5,7 @@
 #include <string.h>
 #include <stdio.h>
 #include <stdlib.h>
-#include "knn_tc.cuh"
+#include "knn_tc4.cuh"
 
 namespace dgcn {
 
@@ -167,7 +167,13 @@ static int launch_knn_tc(KnnArgs& a, Workspace& ws, cudaStream_t stream, const f
     t.work_bytes = static_cast<int>(tc_work_bytes(kp, a.k, t.wide != 0, nch));
     const size_t smem = static_cast<size_t>(t.work_bytes) + sizeof(TcTail) + 1024;
     const bool packed = N <= 4096;
+    // four query tiles per CTA, warp specialised (knn_tc4.cuh), where its smaller work area and fixed consumer fit
+    const bool train = a.epi.mode == EPI_EDGE && a.epi.norm == DGCN_NORM_BATCH_TRAIN;
+    const bool quad = !a.tc_tile_per_cta && packed && t.wide && !train && t.xt32 && (C & 7) == 0 && knn_tc4_list_ok(kp, a.k);
     int rc;
+    if (quad) {
+      rc = launch_knn_tc4(kp, t, dim3(static_cast<unsigned>(ceil_div(N / TILE, T4_GROUPS)), B), stream);
+    } else
     switch (kp) {
       case 16: rc = launch_knn_tc_kp16(packed, t, grid, smem, stream); break;
       case 28: rc = launch_knn_tc_kp28(packed, t, grid, smem, stream); break;
@@ -345,6 +351,7 @@ int fill_knn_args(KnnArgs& a, const float* x, int64_t B, int64_t C, int64_t N, i
   a.K = static_cast<int>(K); a.k = static_cast<int>(dil->k); a.dilation = static_cast<int>(dil->dilation);
   a.exclude_self = exclude_self ? 1 : 0;
   a.exact_fp32 = (dil->flags & DGCN_KNN_EXACT_FP32) ? 1 : 0;
+  a.tc_tile_per_cta = (dil->flags & DGCN_KNN_TC_TILE_PER_CTA) ? 1 : 0;
   a.has_cols = dil->cols_host ? 1 : 0;
   for (int l = 0; l < MAX_KEEP; ++l) a.cols[l] = 0;
   if (dil->cols_host) {

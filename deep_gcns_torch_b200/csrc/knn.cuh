@@ -59,6 +59,7 @@ struct KnnArgs {
   const float* sq;          // (B,N) squared norms
   int K, k, dilation, has_cols, exclude_self;
   int exact_fp32;           // dgcn_dilation.flags & DGCN_KNN_EXACT_FP32 (host-side routing only)
+  int tc_tile_per_cta;      // dgcn_dilation.flags & DGCN_KNN_TC_TILE_PER_CTA (host-side routing only)
   int cols[MAX_KEEP];
   Epilogue epi;
 };
@@ -298,9 +299,11 @@ __host__ __device__ __forceinline__ bool epilogue_wide_ok(const KnnArgs& a) {
 template <int NW, bool TRAIN>
 __device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q0, const uint64_t* list,
                                                   const unsigned char* ok, int* sel, int sel_ld, float* red,
-                                                  int cta) {
+                                                  int cta, int tid) {
+  // tid: index of the calling thread inside the NW-warp team that owns the 128 queries (threadIdx.x when the
+  // team is the CTA; the four-tile kernel passes the index inside the warpgroup).  TRAIN syncs the whole CTA.
   const Epilogue& e = a.epi;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = tid & 31, warp = tid >> 5;
   const int N = a.N, k = a.k;
   constexpr int QPW = TILE / NW;            // queries per warp
   static_assert(QPW == 32 || QPW == 16, "wide consumer: a warp owns 32 or 16 queries (8 | QPW / (32 / G) for G = 16, 32)");

@@ -180,6 +180,20 @@ __device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
                : "memory");
 }
 
+// 32 lanes x 8 consecutive fp32 columns, NOT waited for (see tmem_ld16_async)
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait8(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
+
 // Shared-memory matrix descriptor, MN-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
 // [0,14) start>>4 | [16,30) leading-dim byte offset>>4 = stride between 128-byte MN blocks |
 // [32,46) stride byte offset>>4 = stride between groups of 8 K rows | [46,48) version=1 |
@@ -829,9 +843,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) knn_tc_kernel(const __grid_cons
   const int cta = blockIdx.y * gridDim.x + blockIdx.x;
   if (t.wide) {
     if (a.epi.mode == EPI_EDGE && a.epi.norm == DGCN_NORM_BATCH_TRAIN)
-      cta_epilogue_wide<TC_THREADS / 32, true>(a, b, q0, list, sm.ok, sel, sel_ld, scratch, cta);
+      cta_epilogue_wide<TC_THREADS / 32, true>(a, b, q0, list, sm.ok, sel, sel_ld, scratch, cta, tid);
     else
-      cta_epilogue_wide<TC_THREADS / 32, false>(a, b, q0, list, sm.ok, sel, sel_ld, scratch, cta);
+      cta_epilogue_wide<TC_THREADS / 32, false>(a, b, q0, list, sm.ok, sel, sel_ld, scratch, cta, tid);
   } else {
     float* stage_max = scratch;
     float* stage_min = stage_max + 32 * STAGE_LD + 32;

@@ -1,0 +1,438 @@
+// Four-tile variant of the tensor-core kNN selection (knn_tc.cuh): ONE CTA per SM, warp specialised.
+//
+//   Why: knn_tc_kernel is bound by per-warp instruction latency at 8 warps per SM (255 registers, two CTAs whose
+//   TMEM accumulators fill the 512 columns) and 512 query tiles on 296 CTA slots are 1.73 waves.  Here a CTA is
+//   four warpgroups (16 filter warps, <= 120 registers each) + one producer warp; the four warpgroups own four
+//   128-query tiles of the SAME cloud, so a candidate tile is brought in once (TMA) and multiplied against four
+//   resident query operands; B*N/512 CTAs are a single wave on the 148 SMs for the headline shape.
+//
+//   producer warp (lane 0)   TMA: query planes of the four tiles once, then 64-candidate half-tiles into a
+//                            two-stage ring (stage of half-tile h+1 is refilled as soon as the MMAs of h-1 have
+//                            completed - tcgen05.commit on stage_free);  MMA: per half-tile and group
+//                            3*Cpad/16 + 1 tcgen05.mma (M=128, N=64, K=16) into one of the group's two 64-column
+//                            TMEM accumulators, issued to whichever group has drained that accumulator first
+//                            (non-blocking mbarrier tests), commit -> acc_full[g][h&1].
+//   filter warpgroup g       thread r = TMEM lane r = query r of tile g: wait acc_full, tcgen05.ld 16 columns
+//                            ahead, threshold test -> private candidate buffer (shared memory, slot-major);
+//                            the accumulator is handed back (acc_free) as soon as its last chunk sits in
+//                            registers.  FLUSH = sorting network instead of one insertion per entry: the batch
+//                            (<= 16 entries per lane) is bitonic-sorted in registers, min-merged against the upper
+//                            half of the 32-entry sorted register list and the list re-sorted by one 32-input
+//                            bitonic merge - a fixed ~450 instructions per warp-wide flush whatever the lanes'
+//                            counts (the insertion loop costs ~80 per ROUND, rounds = the fullest lane's count).
+//                            Then: exact fp32 re-rank, certificate, fused consumer - as in knn_tc_kernel, per
+//                            warpgroup (named barriers), in the group's own (now idle) query-plane memory.
+//
+// Eligibility (host side, launch_knn_tc): packed entries (N <= 4096), K <= 20 (list of 28 or 16), C % 8 == 0,
+// 32-byte aligned node-major copy, wide consumer, no train-mode statistics.  Everything else keeps knn_tc_kernel.
+#pragma once
+#include "knn_tc.cuh"
+
+namespace dgcn {
+
+constexpr int T4_GROUPS = 4;
+constexpr int T4_THREADS = T4_GROUPS * 128 + 128;                // 4 filter warpgroups + the producer warpgroup (one
+                                                                 // working warp; setmaxnreg moves its registers to the filters)
+constexpr int T4_FILTER_REGS = 112, T4_PRODUCER_REGS = 32;   // 640 x 96 at launch = 512 x 112 + 128 x 32
+constexpr int T4_CT = 64;                                        // candidates per half-tile (UMMA N)
+constexpr int T4_STAGES = 2;
+constexpr int T4_CAP = 24;                                       // candidate-buffer slots per thread
+constexpr int T4_FLUSH_AT = 16;                                  // flush when a lane holds this many (checked every 8 candidates)
+constexpr int T4_LIST = 32;                                      // register list length (power of two >= KP)
+constexpr int T4_QBYTES = TC_PLANES * 2 * TC_MAX_C * 128;        // 32 KB: query planes of one group
+constexpr int T4_STAGE_BYTES = TC_PLANES * TC_MAX_C * 128;       // 16 KB: one 64-candidate half-tile
+constexpr int T4_SX_BYTES = 16 * 128;                            // 2 KB: candidate-side extra K=16 block
+constexpr int T4_CBUF_BYTES = T4_CAP * 128 * 4;                  // 12 KB per group
+constexpr uint32_t T4_SLOT_STRIDE = 128u * 4u;                   // bytes between two slots of one thread
+
+struct T4Tail {
+  uint64_t full[T4_STAGES];               // half-tile operands have landed (TMA complete_tx)
+  uint64_t stage_free[T4_STAGES];         // every MMA reading the stage has completed
+  uint64_t acc_full[T4_GROUPS][2];        // the group's accumulator holds a finished half-tile
+  uint64_t acc_free[T4_GROUPS][2];        // all 128 threads of the group have read it out
+  uint64_t q_full;                        // query planes have landed
+  uint32_t tmem_base;
+  unsigned char ok[T4_GROUPS][TILE];
+};
+
+constexpr size_t T4_SMEM_BYTES = static_cast<size_t>(T4_GROUPS) * T4_QBYTES + T4_STAGES * (T4_STAGE_BYTES + T4_SX_BYTES) +
+                                 TC_XBLOCK_BYTES + static_cast<size_t>(T4_GROUPS) * T4_CBUF_BYTES + sizeof(T4Tail) + 1024;
+
+constexpr uint32_t kIdescBf16MnMn128x64 =
+    (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+// compare-exchange of two register entries (ascending)
+__device__ __forceinline__ void t4_ce(uint32_t& x, uint32_t& y) {
+  const uint32_t lo = min(x, y), hi = max(x, y);
+  x = lo;
+  y = hi;
+}
+// Bitonic sorting network over a register array, ascending.  All indices are compile-time.
+template <int NN>
+__device__ __forceinline__ void t4_sort(uint32_t (&v)[NN]) {
+#pragma unroll
+  for (int k = 2; k <= NN; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < NN; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          if ((i & k) == 0) t4_ce(v[i], v[l]);
+          else t4_ce(v[l], v[i]);
+        }
+      }
+    }
+  }
+}
+// v bitonic -> ascending
+template <int NN>
+__device__ __forceinline__ void t4_merge(uint32_t (&v)[NN]) {
+#pragma unroll
+  for (int j = NN >> 1; j > 0; j >>= 1) {
+#pragma unroll
+    for (int i = 0; i < NN; ++i) {
+      const int l = i ^ j;
+      if (l > i) t4_ce(v[i], v[l]);
+    }
+  }
+}
+__device__ __forceinline__ void t4_group_sync(int g) {
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(128) : "memory");
+}
+
+template <int KP>
+__global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_constant__ TcArgs t) {
+  static_assert(KP <= T4_LIST && (KP & 1) == 0, "list length");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms: 1024-aligned
+  unsigned char* qbase = base;                                              // [group][plane][mn block][Cpad rows][128 B]
+  unsigned char* stage0 = qbase + T4_GROUPS * T4_QBYTES;                    // [stage][plane][Cpad rows][128 B]
+  unsigned char* sx0 = stage0 + T4_STAGES * T4_STAGE_BYTES;                 // [stage][16 rows][128 B]
+  unsigned char* qx = sx0 + T4_STAGES * T4_SX_BYTES;                        // ones block, shared by the groups
+  unsigned char* cbuf0 = qx + TC_XBLOCK_BYTES;                              // [group][slot][128 threads] u32
+  T4Tail& sm = *reinterpret_cast<T4Tail*>(cbuf0 + T4_GROUPS * T4_CBUF_BYTES);
+  const KnnArgs& a = t.a;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int N = a.N, Cpad = t.Cpad;
+  const int qt0 = blockIdx.x * T4_GROUPS;                                   // first query tile of this CTA
+  const int ngroups = min(T4_GROUPS, N / TILE - qt0);
+  const int H = N / T4_CT;
+  const int plane_q = 2 * Cpad * 128, plane_c = Cpad * 128;
+
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&t.tm_planes)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&t.tm_sqp)) : "memory");
+    for (int s = 0; s < T4_STAGES; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.stage_free[s], 1);
+    }
+    for (int g = 0; g < T4_GROUPS; ++g)
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&sm.acc_full[g][i], 1);
+        mbar_init(&sm.acc_free[g][i], 128);
+      }
+    mbar_init(&sm.q_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // constant operand blocks: ones in K rows 0..2 on the query side; the candidate-side blocks are zero in rows
+  // 8..15 (TMA refreshes rows 0..7 of a stage with every half-tile).  Whole rows are constant: no swizzle needed.
+  for (int ch = tid; ch < TC_XBLOCK_BYTES / 16; ch += T4_THREADS) {
+    const int row = (ch >> 3) & 15;
+    const uint32_t one2 = row < 3 ? 0x3F803F80u : 0u;
+    reinterpret_cast<uint4*>(qx)[ch] = make_uint4(one2, one2, one2, one2);
+  }
+  for (int ch = tid; ch < T4_STAGES * T4_SX_BYTES / 16; ch += T4_THREADS)
+    reinterpret_cast<uint4*>(sx0)[ch] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  __syncthreads();
+  if (warp == T4_GROUPS * 4) {
+    __syncwarp();
+    tmem_alloc(&sm.tmem_base, 512);     // 4 groups x 2 accumulators x 64 columns
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp >= T4_GROUPS * 4) {
+    // ================================ producer ================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T4_PRODUCER_REGS));
+    if (warp == T4_GROUPS * 4 && lane == 0) {
+      mbar_expect_tx(&sm.q_full, static_cast<uint32_t>(ngroups * 2 * plane_q));
+      for (int g = 0; g < ngroups; ++g)
+#pragma unroll
+        for (int pl = 0; pl < TC_PLANES; ++pl)
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk)
+            tma_load_2d(smem_u32(qbase + g * T4_QBYTES) + pl * plane_q + blk * (Cpad * 128), &t.tm_planes,
+                        (qt0 + g) * TILE + blk * 64, (b * TC_PLANES + pl) * Cpad, &sm.q_full);
+      const uint32_t tile_bytes = static_cast<uint32_t>(2 * plane_c + 8 * 128);
+      auto tma_tile = [&](int h) {
+        const int s = h & 1;
+        mbar_expect_tx(&sm.full[s], tile_bytes);
+#pragma unroll
+        for (int pl = 0; pl < TC_PLANES; ++pl)
+          tma_load_2d(smem_u32(stage0 + s * T4_STAGE_BYTES) + pl * plane_c, &t.tm_planes, h * T4_CT,
+                      (b * TC_PLANES + pl) * Cpad, &sm.full[s]);
+        tma_load_2d(smem_u32(sx0 + s * T4_SX_BYTES), &t.tm_sqp, h * T4_CT, b * 8, &sm.full[s]);
+      };
+      tma_tile(0);
+      mbar_wait(&sm.q_full, 0u);
+      const uint64_t dqx = umma_desc_mn_sw128(smem_u32(qx), 2048, 1024);
+      for (int h = 0; h < H; ++h) {
+        const int s = h & 1;
+        if (h + 1 < H) {
+          if (h >= 1) mbar_wait(&sm.stage_free[s ^ 1], static_cast<uint32_t>(((h - 1) >> 1) & 1));
+          tma_tile(h + 1);
+        }
+        mbar_wait(&sm.full[s], static_cast<uint32_t>((h >> 1) & 1));
+        const uint32_t bbase = smem_u32(stage0 + s * T4_STAGE_BYTES);
+        const uint64_t dsx = umma_desc_mn_sw128(smem_u32(sx0 + s * T4_SX_BYTES), 2048, 1024);
+        uint32_t pending = (1u << ngroups) - 1u;
+        for (uint32_t spin = 0; pending; ++spin) {
+          for (int g = 0; g < ngroups; ++g) {
+            if (!((pending >> g) & 1u)) continue;
+            if (h >= 2 && !mbar_test(&sm.acc_free[g][s], static_cast<uint32_t>(((h >> 1) - 1) & 1))) continue;
+            tc_fence_after();
+            const uint32_t tacc = tmem + static_cast<uint32_t>(g * 128 + s * T4_CT);
+            const uint32_t abase = smem_u32(qbase + g * T4_QBYTES);
+            uint32_t acc = 0;
+            for (int kk = 0; kk < Cpad / 16; ++kk) {
+              // hi*hi, hi*mid, mid*hi  (mid*mid <= 2^-16 |x_i||x_j| is inside eps)
+              const uint32_t a_hi = abase + kk * 2048, a_mid = abase + plane_q + kk * 2048;
+              const uint32_t b_hi = bbase + kk * 2048, b_mid = bbase + plane_c + kk * 2048;
+              umma_bf16(tacc, umma_desc_mn_sw128(a_hi, Cpad * 128, 1024), umma_desc_mn_sw128(b_hi, Cpad * 128, 1024),
+                        kIdescBf16MnMn128x64, acc);
+              umma_bf16(tacc, umma_desc_mn_sw128(a_hi, Cpad * 128, 1024), umma_desc_mn_sw128(b_mid, Cpad * 128, 1024),
+                        kIdescBf16MnMn128x64, 1u);
+              umma_bf16(tacc, umma_desc_mn_sw128(a_mid, Cpad * 128, 1024), umma_desc_mn_sw128(b_hi, Cpad * 128, 1024),
+                        kIdescBf16MnMn128x64, 1u);
+              acc = 1;
+            }
+            umma_bf16(tacc, dqx, dsx, kIdescBf16MnMn128x64, 1u);   // + 1 x (-|x_j|^2/2)
+            umma_commit(&sm.acc_full[g][s]);
+            pending &= ~(1u << g);
+          }
+          if (spin > (1u << 26)) __trap();
+        }
+        umma_commit(&sm.stage_free[s]);
+      }
+    }
+    __syncwarp();
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T4_FILTER_REGS));
+    if ((warp >> 2) < ngroups) {
+    // ================================ filter warpgroup ================================
+    const int g = warp >> 2;
+    const int r = tid & 127;                               // query row of the tile = TMEM lane
+    const int q0 = (qt0 + g) * TILE, qg = q0 + r;
+    const float* sqb = a.sq + static_cast<int64_t>(b) * N;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    uint32_t lk[T4_LIST];                                  // ascending packed entries (key bits | 12-bit index)
+#pragma unroll
+    for (int i = 0; i < T4_LIST; ++i) lk[i] = 0xFFFFFFFFu;
+    const float sqq = __ldg(sqb + qg);
+    float tau_f = __uint_as_float(0x7FC00000u);            // NaN admits everything until the list is full
+    float thr_acc = tau_f;
+    const uint32_t cb_addr0 = smem_u32(cbuf0 + g * T4_CBUF_BYTES) + static_cast<uint32_t>(r) * 4u;
+    uint32_t cb_addr = cb_addr0;
+
+    // entry = accumulator bits (acc = -key/2) with the low 12 mantissa bits replaced by the index -> packed list
+    // entry: (bits of an UPPER bound of the squared distance's lower bound ... ) exactly as knn_tc_kernel's flush
+    auto unpack = [&](uint32_t en) -> uint32_t {
+      const uint32_t ab = (en & 0x80000000u) ? (en & 0xFFFFF000u) : (en | 0xFFFu);
+      const float d2 = fmaxf(fmaf(-2.0f, __uint_as_float(ab), sqq), 0.f);
+      return (__float_as_uint(d2) & 0xFFFFF000u) | (en & 0xFFFu);
+    };
+    auto ld_slot = [&](int e) -> uint32_t {
+      uint32_t v;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(cb_addr0 + static_cast<uint32_t>(e) * T4_SLOT_STRIDE));
+      return v;
+    };
+    // Warp-synchronous flush by sorting network (see the header comment).
+    auto flush = [&]() {
+      const int cnt = static_cast<int>((cb_addr - cb_addr0) / T4_SLOT_STRIDE);
+      {
+        uint32_t bv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          bv[i] = 0xFFFFFFFFu;
+          if (i < cnt) bv[i] = unpack(ld_slot(i));
+        }
+        t4_sort<16>(bv);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) lk[T4_LIST - 16 + i] = min(lk[T4_LIST - 16 + i], bv[15 - i]);
+        t4_merge<T4_LIST>(lk);
+      }
+      if (__any_sync(0xffffffffu, cnt > 16)) {             // slots 16..23 (a lane can hold 15 + 8 when the check fires)
+        uint32_t bv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          bv[i] = 0xFFFFFFFFu;
+          if (16 + i < cnt) bv[i] = unpack(ld_slot(16 + i));
+        }
+        t4_sort<8>(bv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lk[T4_LIST - 8 + i] = min(lk[T4_LIST - 8 + i], bv[7 - i]);
+        t4_merge<T4_LIST>(lk);
+      }
+      cb_addr = cb_addr0;
+      // admission in key units (distance minus |x_i|^2), one truncation step above the KP-th entry
+      tau_f = lk[KP - 1] == 0xFFFFFFFFu ? __uint_as_float(0x7FC00000u)
+                                        : __uint_as_float((lk[KP - 1] & 0xFFFFF000u) + 0x1000u) - sqq;
+      thr_acc = -0.5f * tau_f;                             // key <= tau  <=>  acc >= -tau/2
+    };
+
+    // Eight candidates: test, buffer; then the flush check.  A macro so that the chunk registers never become an
+    // addressable array.  One LOP3 builds the entry (key & R & I) | (R ^ I), R = ~0xFFF | index bits 4..11,
+    // I = ~0xFFF | index bits 0..3 (immediate).
+#define DGCN_T4_FILTER8(V, OFF, RB)                                                                                   \
+  do {                                                                                                                \
+    _Pragma("unroll") for (int i = (OFF); i < (OFF) + 8; ++i) {                                                       \
+      const uint32_t accb = V[i];                                                                                     \
+      const uint32_t ibits = 0xFFFFF000u | static_cast<uint32_t>(i);                                                  \
+      asm volatile(                                                                                                   \
+          "{\n"                                                                                                       \
+          ".reg .pred p;\n"                                                                                           \
+          ".reg .b32 en;\n"                                                                                           \
+          "lop3.b32 en, %1, %2, %5, 0xE6;\n"                                                                          \
+          "setp.geu.f32 p, %6, %3;\n"                                                                                 \
+          "@p st.shared.b32 [%0], en;\n"                                                                              \
+          "@p add.u32 %0, %0, %4;\n"                                                                                  \
+          "}"                                                                                                         \
+          : "+r"(cb_addr)                                                                                             \
+          : "r"(accb), "r"(RB), "f"(thr_acc), "n"(128 * 4), "r"(ibits), "f"(__uint_as_float(accb)));                  \
+    }                                                                                                                 \
+    if (__any_sync(0xffffffffu, cb_addr - cb_addr0 >= T4_FLUSH_AT * T4_SLOT_STRIDE)) flush();                         \
+  } while (0)
+    // A half-tile is consumed in eight steps of 8 columns, two steps per iteration of a rolled loop (the flush code
+    // exists twice plus the final flush, not once per step: the instruction cache matters at ~700 instructions a copy).
+#pragma unroll 1
+    for (int h = 0; h < H; ++h) {
+      const int ab = h & 1;
+      mbar_wait(&sm.acc_full[g][ab], static_cast<uint32_t>((h >> 1) & 1));
+      tc_fence_after();
+      const uint32_t tacc = tmem + static_cast<uint32_t>(g * 128 + ab * T4_CT) + lane_base;
+      uint32_t va[8], vb[8];
+      __syncwarp();                                        // tcgen05.ld is warp-collective
+      tmem_ld8_async(tacc, va);
+#pragma unroll 1
+      for (int c8 = 0; c8 < T4_CT / 8; c8 += 2) {
+        const uint32_t rbits = 0xFFFFF000u | static_cast<uint32_t>(h * T4_CT + c8 * 8);
+        __syncwarp();
+        tmem_wait8(va);
+        tmem_ld8_async(tacc + static_cast<uint32_t>((c8 + 1) * 8), vb);
+        DGCN_T4_FILTER8(va, 0, rbits);
+        __syncwarp();
+        tmem_wait8(vb);
+        if (c8 + 2 < T4_CT / 8) {
+          tmem_ld8_async(tacc + static_cast<uint32_t>((c8 + 2) * 8), va);
+        } else {
+          tc_fence_before();                               // the whole accumulator sits in registers: hand it back
+          mbar_arrive(&sm.acc_free[g][ab]);
+        }
+        DGCN_T4_FILTER8(vb, 0, rbits + 8u);
+      }
+    }
+#undef DGCN_T4_FILTER8
+    flush();
+    t4_group_sync(g);   // the group's MMAs have completed (every thread saw the last acc_full) and nobody of the
+                        // group flushes any more: its query planes and candidate buffer become the work area
+
+    // ---- exact re-rank of the listed candidates (fp32 FMA chain, channels ascending) --------------------------
+    uint64_t* list = reinterpret_cast<uint64_t*>(qbase + g * T4_QBYTES);   // [KP][TILE]
+    const float cut = (lk[KP - 1] == 0xFFFFFFFFu) ? INFINITY : __uint_as_float(lk[KP - 1] & 0xFFFFF000u);
+    const int C = a.C;
+    const float* xtb = t.xt + static_cast<int64_t>(b) * N * C;
+    const float* xqp = xtb + static_cast<int64_t>(qg) * C;
+    {
+      // Two halves of KP/2 candidates (register budget of a 17-warp CTA).  Channels in chunks of 8 in the outer
+      // loop, candidates in the inner one: KP/2 independent FMA chains in flight; per candidate the chain is
+      // acc = fma(x_q[c], x_j[c], acc) for c ascending from acc = 0 - the bits of the fp32 kernel.
+      constexpr int HN = KP / 2;
+      int e = 0;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float dex[HN];
+#pragma unroll
+        for (int u = 0; u < HN; ++u) dex[u] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < C; c += 8) {
+          float q8[8];
+          ldg256(xqp + c, q8);
+#pragma unroll
+          for (int u = 0; u < HN; ++u) {
+            const uint32_t en = lk[half * HN + u];
+            const uint32_t j = en != 0xFFFFFFFFu ? (en & 0xFFFu) : static_cast<uint32_t>(qg);
+            float w[8];
+            ldg256(xtb + j * static_cast<uint32_t>(C) + c, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dex[u] = fmaf(q8[i], w[i], dex[u]);
+          }
+        }
+        // insertion by exact key into the exact-sorted prefix [0, e)
+#pragma unroll
+        for (int u = 0; u < HN; ++u) {
+          const uint32_t en = lk[half * HN + u];
+          const bool listed = en != 0xFFFFFFFFu;
+          const uint32_t j = en & 0xFFFu;
+          if (listed && !(a.exclude_self && j == static_cast<uint32_t>(qg))) {   // self exclusion (loop=False)
+            const float d = (sqq + (-2.0f * dex[u])) + __ldg(sqb + j);
+            const uint64_t key = make_key(d, j);
+            int i = e;
+            while (i > 0) {
+              const uint64_t prev = list[(i - 1) * TILE + r];
+              if (prev < key) break;
+              list[i * TILE + r] = prev;
+              --i;
+            }
+            list[i * TILE + r] = key;
+            ++e;
+          }
+        }
+      }
+      for (int i = e; i < KP; ++i) list[i * TILE + r] = KEY_MAX;
+    }
+    // ---- certificate (thread = query): see knn_tc_kernel -------------------------------------------------------
+    {
+      const uint64_t kth = list[(a.K - 1) * TILE + r];
+      bool ok = kth != KEY_MAX;
+      if (ok && cut < INFINITY) {
+        const float dk = ordered_to_float(static_cast<uint32_t>(kth >> 32));
+        const float smax = __ldg(t.sqmax + b);
+        const float eps = (2.0f * (3.0518e-5f + (5.0f * Cpad + 8.0f) * 1.1921e-7f)) * sqrtf(sqq * smax) +
+                          9.537e-7f * (sqq + smax);
+        ok = (dk + eps < cut);
+      }
+      sm.ok[g][r] = ok ? 1 : 0;
+      if (!ok) {
+        const int slot = atomicAdd(t.fail_count, 1);
+        t.fail_list[slot] = b * N + qg;
+      }
+    }
+    t4_group_sync(g);
+    // ---- consumer: sel lives in the group's candidate buffer ---------------------------------------------------
+    int* sel = reinterpret_cast<int*>(cbuf0 + g * T4_CBUF_BYTES);
+    cta_epilogue_wide<4, false>(a, b, q0, list, sm.ok[g], sel, tc_sel_ld(a.k), nullptr, 0, r);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();   // every MMA has completed and every accumulator has been read
+  if (warp == T4_GROUPS * 4) tmem_dealloc(tmem, 512);
+}
+
+inline bool knn_tc4_list_ok(int kp, int k) {
+  return (kp == 16 || kp == 28) && static_cast<size_t>(TILE) * tc_sel_ld(k) * 4 <= static_cast<size_t>(T4_CBUF_BYTES);
+}
+
+template <int KP>
+inline int launch_knn_tc4_inst(const TcArgs& t, dim3 grid, cudaStream_t stream) {
+  DGCN_ENSURE_SMEM((knn_tc4_kernel<KP>), T4_SMEM_BYTES);
+  knn_tc4_kernel<KP><<<grid, T4_THREADS, T4_SMEM_BYTES, stream>>>(t);
+  return DGCN_OK;
+}
+int launch_knn_tc4(int kp, const TcArgs& t, dim3 grid, cudaStream_t stream);
+
+}  // namespace dgcn

@@ -91,9 +91,15 @@ typedef struct dgcn_basic_conv {
  * l < k, or - stochastic branch - the k ranks listed in cols_host (a HOST
  * array drawn by the caller from the CPU generator, torch_edge.py:22-24). */
 /* flags: DGCN_KNN_EXACT_FP32 ranks with the fp32 FMA kernels only (no tensor-core
- * pre-filter); the result is the same list either way - the switch exists for A/B
- * tests and measurements and is a property of the CALL, not of the process. */
-enum dgcn_knn_flags { DGCN_KNN_DEFAULT = 0, DGCN_KNN_EXACT_FP32 = 1 };
+ * pre-filter); DGCN_KNN_TC_TILE_PER_CTA keeps the tensor-core pre-filter on the
+ * one-tile-per-CTA kernel where the four-tile warp-specialised kernel would be chosen.
+ * The result is the same list either way - the switches exist for A/B tests and
+ * measurements and are a property of the CALL, not of the process. */
+enum dgcn_knn_flags {
+  DGCN_KNN_DEFAULT = 0,
+  DGCN_KNN_EXACT_FP32 = 1,
+  DGCN_KNN_TC_TILE_PER_CTA = 2 /* tensor-core path: always the one-tile-per-CTA kernel, never the four-tile one */
+};
 typedef struct dgcn_dilation {
   int64_t k;
   int64_t dilation;

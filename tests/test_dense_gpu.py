@@ -428,3 +428,69 @@ def test_block_epilogues_fused_into_the_consumer(cfg):
         with torch.no_grad():
             y_train = blk(x)
         assert y_train.shape == ref.shape and torch.isfinite(y_train).all()
+
+
+@pytest.mark.parametrize("cfg", [
+    # B, C, c_out, N, k, d, conv          (four-tile kernel: C % 8 == 0, K <= 20, c_out in {32, 64, 128})
+    (2, 64, 64, 4096, 20, 1, "edge"),     # the headline layer shape: 8 CTAs x 4 warpgroups per cloud
+    (3, 64, 64, 1024, 10, 2, "edge"),     # dilation inside the kernel's rank selection (K = 20)
+    (2, 32, 128, 640, 9, 1, "edge"),      # list of 16; 5 query tiles: the second CTA runs one warpgroup
+    (1, 16, 32, 384, 16, 1, "edge"),      # 3 query tiles: one CTA with an idle warpgroup
+    (2, 8, 64, 128, 20, 1, "edge"),       # a single query tile, two candidate half-tiles
+    (2, 64, 24, 512, 12, 1, "mr"),        # MRConv consumer (c_in = 64)
+    (1, 40, 64, 2048, 4, 1, "edge"),      # C = 40 -> three K=16 blocks of channels, zero padded
+])
+def test_four_tile_kernel_equals_tile_per_cta_and_fp32_paths(cfg):
+    """knn_tc4_kernel (four query tiles per CTA, producer warp + four filter warpgroups, sorting-network flush)
+    must return the neighbour lists of knn_tc_kernel and of the pure fp32 kernel bit for bit, and the features
+    of knn_tc_kernel bit for bit (same consumer code on the same lists)."""
+    from deep_gcns_torch_b200 import _native
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    B, C, co, N, k, d, conv = cfg
+    g = torch.Generator().manual_seed(N * 7 + C)
+    x = torch.randn(B, C, N, 1, generator=g).cuda()
+    x[0, :, 5] = x[0, :, 9]                                   # exact duplicates: forces ties
+    x[0, :, 17] = x[0, :, 9]
+    torch.manual_seed(1)
+    mod = D.DynConv2d(C, co, k, d, conv, "relu", "batch", True).cuda().eval()
+    graph = D.DenseDilatedKnnGraph(k, d)
+    out = {}
+    try:
+        for path in ("ffma", "tc1", "tc"):
+            _native.set_knn_path(path)
+            with torch.no_grad():
+                out[path] = (graph(x), mod(x))
+    finally:
+        _native.set_knn_path("auto")
+    assert torch.equal(out["tc"][0], out["ffma"][0])
+    assert torch.equal(out["tc"][0], out["tc1"][0])
+    assert torch.equal(out["tc"][1], out["tc1"][1])
+    torch.testing.assert_close(out["tc"][1], out["ffma"][1], rtol=1e-5, atol=1e-6)
+
+
+def test_four_tile_kernel_self_exclusion_clusters_and_block_fusion():
+    """Same kernel: DilatedKnnGraph's self exclusion (applied in the exact re-rank), a clustered cloud whose
+    queries cannot be certified (exact completion kernel), and the fused block epilogue (skip connection +
+    channel-slice store) on top of it."""
+    from deep_gcns_torch_b200 import _native
+    from deep_gcns_torch_b200.gcn_lib import dense as D
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 64, 512, 1, generator=g).cuda()
+    centres = torch.randn(1, 16, 8, generator=g)
+    xc = (centres[:, :, torch.randint(0, 8, (512,), generator=g)] + 1e-6 * torch.randn(1, 16, 512, generator=g))
+    xc = xc.unsqueeze(-1).cuda()
+    torch.manual_seed(2)
+    blk = D.ResDynBlock2d(64, 20, 1, "edge", "relu", "batch", True, res_scale=0.7).cuda().eval()
+    got = {}
+    try:
+        for path in ("ffma", "tc1", "tc"):
+            _native.set_knn_path(path)
+            with torch.no_grad():
+                got[path] = (_native.knn_graph(x, 20, 1, exclude_self=True)[0], D.DenseDilatedKnnGraph(20, 1)(xc), blk(x))
+    finally:
+        _native.set_knn_path("auto")
+    for i in range(2):
+        assert torch.equal(got["tc"][i], got["ffma"][i])
+        assert torch.equal(got["tc"][i], got["tc1"][i])
+    assert torch.equal(got["tc"][2], got["tc1"][2])
+    assert not bool((got["tc"][0][0] == got["tc"][0][1]).any())          # no query lists itself
