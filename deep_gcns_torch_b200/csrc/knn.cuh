@@ -296,7 +296,7 @@ __host__ __device__ __forceinline__ bool epilogue_wide_ok(const KnnArgs& a) {
   return (nch == 32 || nch == 64 || nch == 128) && (a.N & 7) == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0;
 }
 
-template <int NW, bool TRAIN>
+template <int NW, bool TRAIN, bool SEL_READY = false>
 __device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q0, const uint64_t* list,
                                                   const unsigned char* ok, int* sel, int sel_ld, float* red,
                                                   int cta, int tid) {
@@ -308,7 +308,8 @@ __device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q
   constexpr int QPW = TILE / NW;            // queries per warp
   static_assert(QPW == 32 || QPW == 16, "wide consumer: a warp owns 32 or 16 queries (8 | QPW / (32 / G) for G = 16, 32)");
   const int64_t node0 = static_cast<int64_t>(b) * N;
-  for (int qq = 0; qq < QPW; ++qq) {
+  // SEL_READY: the caller has filled sel (the k neighbours of every live query, any order) and wants no index output
+  for (int qq = 0; qq < (SEL_READY ? 0 : QPW); ++qq) {
     const int ql = warp * QPW + qq;
     const int qg = q0 + ql;
     const bool live = qg < N && ok[ql];

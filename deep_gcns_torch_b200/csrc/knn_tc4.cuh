@@ -97,6 +97,18 @@ __device__ __forceinline__ void t4_merge(uint32_t (&v)[NN]) {
     }
   }
 }
+// true on exactly one lane of the (converged) warp
+__device__ __forceinline__ bool t4_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void t4_group_sync(int g) {
   asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(128) : "memory");
 }
@@ -126,7 +138,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&t.tm_sqp)) : "memory");
     for (int s = 0; s < T4_STAGES; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.stage_free[s], 1);
+      mbar_init(&sm.stage_free[s], static_cast<uint32_t>(ngroups));
     }
     for (int g = 0; g < T4_GROUPS; ++g)
       for (int i = 0; i < 2; ++i) {
@@ -157,9 +169,25 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
   const uint32_t tmem = sm.tmem_base;
 
   if (warp >= T4_GROUPS * 4) {
-    // ================================ producer ================================
+    // ================================ producers ================================
+    // Producer warp pw issues the MMAs of warpgroup pw (tcgen05.commit tracks the issuing thread's own MMAs, so the
+    // four chains are independent); warp 0 of them also moves the operands.  Control flow stays warp-uniform - every
+    // lane waits on the barriers and computes the (uniform) descriptors, one elected lane issues - so that the
+    // descriptors live in uniform registers instead of being rebuilt lane by lane around every tcgen05.mma.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T4_PRODUCER_REGS));
-    if (warp == T4_GROUPS * 4 && lane == 0) {
+    const int pw = warp - T4_GROUPS * 4;
+    const bool leader = t4_elect_one();
+    const uint32_t tile_bytes = static_cast<uint32_t>(2 * plane_c + 8 * 128);
+    auto tma_tile = [&](int h) {                           // elected lane of producer warp 0
+      const int s = h & 1;
+      mbar_expect_tx(&sm.full[s], tile_bytes);
+#pragma unroll
+      for (int pl = 0; pl < TC_PLANES; ++pl)
+        tma_load_2d(smem_u32(stage0 + s * T4_STAGE_BYTES) + pl * plane_c, &t.tm_planes, h * T4_CT,
+                    (b * TC_PLANES + pl) * Cpad, &sm.full[s]);
+      tma_load_2d(smem_u32(sx0 + s * T4_SX_BYTES), &t.tm_sqp, h * T4_CT, b * 8, &sm.full[s]);
+    };
+    if (pw == 0 && leader) {
       mbar_expect_tx(&sm.q_full, static_cast<uint32_t>(ngroups * 2 * plane_q));
       for (int g = 0; g < ngroups; ++g)
 #pragma unroll
@@ -168,56 +196,48 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
           for (int blk = 0; blk < 2; ++blk)
             tma_load_2d(smem_u32(qbase + g * T4_QBYTES) + pl * plane_q + blk * (Cpad * 128), &t.tm_planes,
                         (qt0 + g) * TILE + blk * 64, (b * TC_PLANES + pl) * Cpad, &sm.q_full);
-      const uint32_t tile_bytes = static_cast<uint32_t>(2 * plane_c + 8 * 128);
-      auto tma_tile = [&](int h) {
-        const int s = h & 1;
-        mbar_expect_tx(&sm.full[s], tile_bytes);
-#pragma unroll
-        for (int pl = 0; pl < TC_PLANES; ++pl)
-          tma_load_2d(smem_u32(stage0 + s * T4_STAGE_BYTES) + pl * plane_c, &t.tm_planes, h * T4_CT,
-                      (b * TC_PLANES + pl) * Cpad, &sm.full[s]);
-        tma_load_2d(smem_u32(sx0 + s * T4_SX_BYTES), &t.tm_sqp, h * T4_CT, b * 8, &sm.full[s]);
-      };
       tma_tile(0);
+    }
+    __syncwarp();
+    if (pw < ngroups) {
+      const int g = pw;
       mbar_wait(&sm.q_full, 0u);
       const uint64_t dqx = umma_desc_mn_sw128(smem_u32(qx), 2048, 1024);
+      const uint32_t abase = smem_u32(qbase + g * T4_QBYTES);
+      const int ksteps = Cpad / 16;
+#pragma unroll 1
       for (int h = 0; h < H; ++h) {
         const int s = h & 1;
-        if (h + 1 < H) {
+        if (pw == 0 && h + 1 < H) {                        // refill the other stage: its MMAs (half-tile h-1) must be done
           if (h >= 1) mbar_wait(&sm.stage_free[s ^ 1], static_cast<uint32_t>(((h - 1) >> 1) & 1));
-          tma_tile(h + 1);
+          if (leader) tma_tile(h + 1);
+          __syncwarp();
         }
         mbar_wait(&sm.full[s], static_cast<uint32_t>((h >> 1) & 1));
+        if (h >= 2) mbar_wait(&sm.acc_free[g][s], static_cast<uint32_t>(((h >> 1) - 1) & 1));
+        tc_fence_after();
         const uint32_t bbase = smem_u32(stage0 + s * T4_STAGE_BYTES);
         const uint64_t dsx = umma_desc_mn_sw128(smem_u32(sx0 + s * T4_SX_BYTES), 2048, 1024);
-        uint32_t pending = (1u << ngroups) - 1u;
-        for (uint32_t spin = 0; pending; ++spin) {
-          for (int g = 0; g < ngroups; ++g) {
-            if (!((pending >> g) & 1u)) continue;
-            if (h >= 2 && !mbar_test(&sm.acc_free[g][s], static_cast<uint32_t>(((h >> 1) - 1) & 1))) continue;
-            tc_fence_after();
-            const uint32_t tacc = tmem + static_cast<uint32_t>(g * 128 + s * T4_CT);
-            const uint32_t abase = smem_u32(qbase + g * T4_QBYTES);
-            uint32_t acc = 0;
-            for (int kk = 0; kk < Cpad / 16; ++kk) {
-              // hi*hi, hi*mid, mid*hi  (mid*mid <= 2^-16 |x_i||x_j| is inside eps)
-              const uint32_t a_hi = abase + kk * 2048, a_mid = abase + plane_q + kk * 2048;
-              const uint32_t b_hi = bbase + kk * 2048, b_mid = bbase + plane_c + kk * 2048;
-              umma_bf16(tacc, umma_desc_mn_sw128(a_hi, Cpad * 128, 1024), umma_desc_mn_sw128(b_hi, Cpad * 128, 1024),
-                        kIdescBf16MnMn128x64, acc);
-              umma_bf16(tacc, umma_desc_mn_sw128(a_hi, Cpad * 128, 1024), umma_desc_mn_sw128(b_mid, Cpad * 128, 1024),
-                        kIdescBf16MnMn128x64, 1u);
-              umma_bf16(tacc, umma_desc_mn_sw128(a_mid, Cpad * 128, 1024), umma_desc_mn_sw128(b_hi, Cpad * 128, 1024),
-                        kIdescBf16MnMn128x64, 1u);
-              acc = 1;
-            }
-            umma_bf16(tacc, dqx, dsx, kIdescBf16MnMn128x64, 1u);   // + 1 x (-|x_j|^2/2)
-            umma_commit(&sm.acc_full[g][s]);
-            pending &= ~(1u << g);
+        const uint32_t tacc = tmem + static_cast<uint32_t>(g * 128 + s * T4_CT);
+        // descriptors differ only in the start-address field (bits 0..13 = address >> 4)
+        const uint64_t da_hi0 = umma_desc_mn_sw128(abase, Cpad * 128, 1024);
+        const uint64_t da_mid0 = umma_desc_mn_sw128(abase + plane_q, Cpad * 128, 1024);
+        const uint64_t db_hi0 = umma_desc_mn_sw128(bbase, Cpad * 128, 1024);
+        const uint64_t db_mid0 = umma_desc_mn_sw128(bbase + plane_c, Cpad * 128, 1024);
+        if (leader) {
+#pragma unroll 1
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t step = static_cast<uint64_t>(kk) * (2048 >> 4);   // (start addresses stay below 2^18: no carry out of the field)
+            // hi*hi, hi*mid, mid*hi  (mid*mid <= 2^-16 |x_i||x_j| is inside eps)
+            umma_bf16(tacc, da_hi0 + step, db_hi0 + step, kIdescBf16MnMn128x64, kk > 0 ? 1u : 0u);
+            umma_bf16(tacc, da_hi0 + step, db_mid0 + step, kIdescBf16MnMn128x64, 1u);
+            umma_bf16(tacc, da_mid0 + step, db_hi0 + step, kIdescBf16MnMn128x64, 1u);
           }
-          if (spin > (1u << 26)) __trap();
+          umma_bf16(tacc, dqx, dsx, kIdescBf16MnMn128x64, 1u);   // + 1 x (-|x_j|^2/2)
+          umma_commit(&sm.acc_full[g][s]);
+          umma_commit(&sm.stage_free[s]);                  // one arrival per active group completes the phase
         }
-        umma_commit(&sm.stage_free[s]);
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -341,12 +361,94 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
     t4_group_sync(g);   // the group's MMAs have completed (every thread saw the last acc_full) and nobody of the
                         // group flushes any more: its query planes and candidate buffer become the work area
 
-    // ---- exact re-rank of the listed candidates (fp32 FMA chain, channels ascending) --------------------------
-    uint64_t* list = reinterpret_cast<uint64_t*>(qbase + g * T4_QBYTES);   // [KP][TILE]
     const float cut = (lk[KP - 1] == 0xFFFFFFFFu) ? INFINITY : __uint_as_float(lk[KP - 1] & 0xFFFFF000u);
     const int C = a.C;
     const float* xtb = t.xt + static_cast<int64_t>(b) * N * C;
     const float* xqp = xtb + static_cast<int64_t>(qg) * C;
+    const float smax = __ldg(t.sqmax + b);
+    // |approx - exact fp32| <= eps: see the certificate of knn_tc_kernel
+    const float eps = (2.0f * (3.0518e-5f + (5.0f * Cpad + 8.0f) * 1.1921e-7f)) * sqrtf(sqq * smax) +
+                      9.537e-7f * (sqq + smax);
+    int* sel = reinterpret_cast<int*>(cbuf0 + g * T4_CBUF_BYTES);
+    const int sel_ld = tc_sel_ld(a.k);
+    // The consumer reduces over the SET of the K nearest (max over neighbours) when every rank is kept and nobody
+    // asked for the index lists: then only membership matters, and exact arithmetic is needed only where the
+    // approximate ranking cannot decide it.
+    const bool set_only = !a.has_cols && a.dilation == 1 && !a.exclude_self && a.epi.mode != EPI_INDEX &&
+                          a.epi.nbr == nullptr && a.epi.edge_index == nullptr;
+    if (set_only) {
+      // ---- membership by interval arithmetic, exact fp32 chains only inside the ambiguous band --------------------
+      // A list entry a_c (its 20 value bits) is a LOWER bound of the approximate squared distance with
+      // a_c <= approx_c <= a_c + delta(a_c), delta(v) = 2^-10 (v + |x_i|^2) (12 accumulator bits + 12 distance bits
+      // dropped by the packing), and |approx_c - exact_c| <= eps.  With the list ascending in a and vK, vK1 the values
+      // at ranks K and K+1 (1-based): every entry below  lo = vK1 - delta(vK1) - 2 eps  beats all but at most K-1
+      // candidates (certainly IN), every entry - and every unlisted candidate, whose approximation is >= cut - above
+      // hi = vK + delta(vK) + 2 eps  is beaten by K candidates (certainly OUT).  What lies in [lo, hi] is ranked by
+      // the exact key (fp32 FMA chain, ties to the smaller index) and fills the remaining places.
+      constexpr int MB = 12;                                           // band entries a query may hold
+      uint64_t* band = reinterpret_cast<uint64_t*>(qbase + g * T4_QBYTES);   // [MB][TILE] exact keys
+      const int K = a.K;
+      float vK = INFINITY, vK1 = INFINITY;
+#pragma unroll
+      for (int u = 0; u < KP; ++u) {
+        const float v = lk[u] == 0xFFFFFFFFu ? INFINITY : __uint_as_float(lk[u] & 0xFFFFF000u);
+        if (u == K - 1) vK = v;
+        if (u == K) vK1 = v;
+      }
+      const float hi = vK + 9.765625e-4f * (vK + sqq) + 2.0f * eps;
+      const float lo = vK1 - 9.765625e-4f * (vK1 + sqq) - 2.0f * eps;
+      bool ok = vK < INFINITY && (cut == INFINITY || hi < cut);
+      int* selrow = sel + r * sel_ld;
+      int n_in = 0, nb = 0;
+#pragma unroll
+      for (int u = 0; u < KP; ++u) {
+        const float v = lk[u] == 0xFFFFFFFFu ? INFINITY : __uint_as_float(lk[u] & 0xFFFFF000u);
+        const uint32_t j = lk[u] & 0xFFFu;
+        const bool in = v < lo;                                        // the list ascends: a prefix
+        const bool bnd = ok && !in && v <= hi;
+        if (in && u < K) {
+          selrow[u] = static_cast<int>(j);
+          n_in = u + 1;
+        }
+        if (__any_sync(0xffffffffu, bnd)) {
+          const uint32_t jj = bnd ? j : static_cast<uint32_t>(qg);     // idle lanes read their own row
+          float dot = 0.f;
+#pragma unroll 2
+          for (int c = 0; c < C; c += 8) {
+            float q8[8], w[8];
+            ldg256(xqp + c, q8);
+            ldg256(xtb + jj * static_cast<uint32_t>(C) + c, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dot = fmaf(q8[i], w[i], dot);
+          }
+          if (bnd) {
+            const float d = (sqq + (-2.0f * dot)) + __ldg(sqb + j);
+            if (nb < MB) band[nb * TILE + r] = make_key(d, j);
+            ++nb;
+          }
+        }
+      }
+      if (nb > MB) ok = false;                                         // a cluster of near ties: exact completion kernel
+      if (ok) {
+        const int need = K - n_in;                                     // 0 <= need <= nb
+        int pos = n_in;
+        for (int i = 0; i < nb; ++i) {
+          const uint64_t ki = band[i * TILE + r];
+          int rank = 0;
+          for (int i2 = 0; i2 < nb; ++i2) rank += band[i2 * TILE + r] < ki ? 1 : 0;
+          if (rank < need) selrow[pos++] = static_cast<int>(static_cast<uint32_t>(ki));
+        }
+      }
+      sm.ok[g][r] = ok ? 1 : 0;
+      if (!ok) {
+        const int slot = atomicAdd(t.fail_count, 1);
+        t.fail_list[slot] = b * N + qg;
+      }
+      t4_group_sync(g);
+      cta_epilogue_wide<4, false, true>(a, b, q0, nullptr, sm.ok[g], sel, sel_ld, nullptr, 0, r);
+    } else {
+    // ---- exact re-rank of the listed candidates (fp32 FMA chain, channels ascending) --------------------------
+    uint64_t* list = reinterpret_cast<uint64_t*>(qbase + g * T4_QBYTES);   // [KP][TILE]
     {
       // Two halves of KP/2 candidates (register budget of a 17-warp CTA).  Channels in chunks of 8 in the outer
       // loop, candidates in the inner one: KP/2 independent FMA chains in flight; per candidate the chain is
@@ -401,9 +503,6 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
       bool ok = kth != KEY_MAX;
       if (ok && cut < INFINITY) {
         const float dk = ordered_to_float(static_cast<uint32_t>(kth >> 32));
-        const float smax = __ldg(t.sqmax + b);
-        const float eps = (2.0f * (3.0518e-5f + (5.0f * Cpad + 8.0f) * 1.1921e-7f)) * sqrtf(sqq * smax) +
-                          9.537e-7f * (sqq + smax);
         ok = (dk + eps < cut);
       }
       sm.ok[g][r] = ok ? 1 : 0;
@@ -414,8 +513,8 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
     }
     t4_group_sync(g);
     // ---- consumer: sel lives in the group's candidate buffer ---------------------------------------------------
-    int* sel = reinterpret_cast<int*>(cbuf0 + g * T4_CBUF_BYTES);
-    cta_epilogue_wide<4, false>(a, b, q0, list, sm.ok[g], sel, tc_sel_ld(a.k), nullptr, 0, r);
+    cta_epilogue_wide<4, false>(a, b, q0, list, sm.ok[g], sel, sel_ld, nullptr, 0, r);
+    }
     }
   }
   tc_fence_before();

@@ -481,16 +481,20 @@ def test_four_tile_kernel_self_exclusion_clusters_and_block_fusion():
     xc = xc.unsqueeze(-1).cuda()
     torch.manual_seed(2)
     blk = D.ResDynBlock2d(64, 20, 1, "edge", "relu", "batch", True, res_scale=0.7).cuda().eval()
-    got = {}
+    conv_c = D.DynConv2d(16, 32, 20, 1, "edge", "relu", "batch", True).cuda().eval()   # set-only membership path on
+    got = {}                                                                            # the clustered cloud
     try:
         for path in ("ffma", "tc1", "tc"):
             _native.set_knn_path(path)
             with torch.no_grad():
-                got[path] = (_native.knn_graph(x, 20, 1, exclude_self=True)[0], D.DenseDilatedKnnGraph(20, 1)(xc), blk(x))
+                got[path] = (_native.knn_graph(x, 20, 1, exclude_self=True)[0], D.DenseDilatedKnnGraph(20, 1)(xc), blk(x),
+                             conv_c(xc))
     finally:
         _native.set_knn_path("auto")
     for i in range(2):
         assert torch.equal(got["tc"][i], got["ffma"][i])
         assert torch.equal(got["tc"][i], got["tc1"][i])
     assert torch.equal(got["tc"][2], got["tc1"][2])
+    assert torch.equal(got["tc"][3], got["tc1"][3])
+    torch.testing.assert_close(got["tc"][3], got["ffma"][3], rtol=1e-5, atol=1e-6)
     assert not bool((got["tc"][0][0] == got["tc"][0][1]).any())          # no query lists itself
