@@ -44,6 +44,7 @@ constexpr int T4_STAGE_BYTES = TC_PLANES * TC_MAX_C * 128;       // 16 KB: one 6
 constexpr int T4_SX_BYTES = 16 * 128;                            // 2 KB: candidate-side extra K=16 block
 constexpr int T4_CBUF_BYTES = T4_CAP * 128 * 4;                  // 12 KB per group
 constexpr uint32_t T4_SLOT_STRIDE = 128u * 4u;                   // bytes between two slots of one thread
+static_assert(T4_SLOT_STRIDE == 512u, "the filter's asm bumps the slot pointer by the literal 512");
 
 struct T4Tail {
   uint64_t full[T4_STAGES];               // half-tile operands have landed (TMA complete_tx)
@@ -305,26 +306,30 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
       thr_acc = -0.5f * tau_f;                             // key <= tau  <=>  acc >= -tau/2
     };
 
-    // Eight candidates: test, buffer; then the flush check.  A macro so that the chunk registers never become an
-    // addressable array.  One LOP3 builds the entry (key & R & I) | (R ^ I), R = ~0xFFF | index bits 4..11,
-    // I = ~0xFFF | index bits 0..3 (immediate).
-#define DGCN_T4_FILTER8(V, OFF, RB)                                                                                   \
+    // Eight candidates: test, buffer; then the flush check.  ONE asm statement (the compiler cannot thread register
+    // copies of the slot pointer through it) and a macro (the chunk registers never become an addressable array).
+    // Per candidate: one LOP3 builds the entry (key & R & I) | (R ^ I), R = ~0xFFF | index bits 3..11,
+    // I = ~0xFFF | index bits 0..2 (immediate); FSETP; predicated STS + pointer bump.
+#define DGCN_T4_FILTER8(V, RB)                                                                                        \
   do {                                                                                                                \
-    _Pragma("unroll") for (int i = (OFF); i < (OFF) + 8; ++i) {                                                       \
-      const uint32_t accb = V[i];                                                                                     \
-      const uint32_t ibits = 0xFFFFF000u | static_cast<uint32_t>(i);                                                  \
-      asm volatile(                                                                                                   \
-          "{\n"                                                                                                       \
-          ".reg .pred p;\n"                                                                                           \
-          ".reg .b32 en;\n"                                                                                           \
-          "lop3.b32 en, %1, %2, %5, 0xE6;\n"                                                                          \
-          "setp.geu.f32 p, %6, %3;\n"                                                                                 \
-          "@p st.shared.b32 [%0], en;\n"                                                                              \
-          "@p add.u32 %0, %0, %4;\n"                                                                                  \
-          "}"                                                                                                         \
-          : "+r"(cb_addr)                                                                                             \
-          : "r"(accb), "r"(RB), "f"(thr_acc), "n"(128 * 4), "r"(ibits), "f"(__uint_as_float(accb)));                  \
-    }                                                                                                                 \
+    asm volatile(                                                                                                     \
+        "{\n"                                                                                                         \
+        ".reg .pred p;\n"                                                                                             \
+        ".reg .b32 en;\n"                                                                                             \
+        "lop3.b32 en, %1, %17, 0xFFFFF000, 0xE6;\n setp.geu.f32 p, %9, %18;\n @p st.shared.b32 [%0], en;\n @p add.u32 %0, %0, 512;\n"  \
+        "lop3.b32 en, %2, %17, 0xFFFFF001, 0xE6;\n setp.geu.f32 p, %10, %18;\n @p st.shared.b32 [%0], en;\n @p add.u32 %0, %0, 512;\n" \
+        "lop3.b32 en, %3, %17, 0xFFFFF002, 0xE6;\n setp.geu.f32 p, %11, %18;\n @p st.shared.b32 [%0], en;\n @p add.u32 %0, %0, 512;\n" \
+        "lop3.b32 en, %4, %17, 0xFFFFF003, 0xE6;\n setp.geu.f32 p, %12, %18;\n @p st.shared.b32 [%0], en;\n @p add.u32 %0, %0, 512;\n" \
+        "lop3.b32 en, %5, %17, 0xFFFFF004, 0xE6;\n setp.geu.f32 p, %13, %18;\n @p st.shared.b32 [%0], en;\n @p add.u32 %0, %0, 512;\n" \
+        "lop3.b32 en, %6, %17, 0xFFFFF005, 0xE6;\n setp.geu.f32 p, %14, %18;\n @p st.shared.b32 [%0], en;\n @p add.u32 %0, %0, 512;\n" \
+        "lop3.b32 en, %7, %17, 0xFFFFF006, 0xE6;\n setp.geu.f32 p, %15, %18;\n @p st.shared.b32 [%0], en;\n @p add.u32 %0, %0, 512;\n" \
+        "lop3.b32 en, %8, %17, 0xFFFFF007, 0xE6;\n setp.geu.f32 p, %16, %18;\n @p st.shared.b32 [%0], en;\n @p add.u32 %0, %0, 512;\n" \
+        "}"                                                                                                           \
+        : "+r"(cb_addr)                                                                                               \
+        : "r"(V[0]), "r"(V[1]), "r"(V[2]), "r"(V[3]), "r"(V[4]), "r"(V[5]), "r"(V[6]), "r"(V[7]),                     \
+          "f"(__uint_as_float(V[0])), "f"(__uint_as_float(V[1])), "f"(__uint_as_float(V[2])),                         \
+          "f"(__uint_as_float(V[3])), "f"(__uint_as_float(V[4])), "f"(__uint_as_float(V[5])),                         \
+          "f"(__uint_as_float(V[6])), "f"(__uint_as_float(V[7])), "r"(RB), "f"(thr_acc));                             \
     if (__any_sync(0xffffffffu, cb_addr - cb_addr0 >= T4_FLUSH_AT * T4_SLOT_STRIDE)) flush();                         \
   } while (0)
     // A half-tile is consumed in eight steps of 8 columns, two steps per iteration of a rolled loop (the flush code
@@ -340,12 +345,11 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
       tmem_ld8_async(tacc, va);
 #pragma unroll 1
       for (int c8 = 0; c8 < T4_CT / 8; c8 += 2) {
+        // (the warp stays converged through this loop: the flush branch is taken on a warp-wide vote)
         const uint32_t rbits = 0xFFFFF000u | static_cast<uint32_t>(h * T4_CT + c8 * 8);
-        __syncwarp();
         tmem_wait8(va);
         tmem_ld8_async(tacc + static_cast<uint32_t>((c8 + 1) * 8), vb);
-        DGCN_T4_FILTER8(va, 0, rbits);
-        __syncwarp();
+        DGCN_T4_FILTER8(va, rbits);
         tmem_wait8(vb);
         if (c8 + 2 < T4_CT / 8) {
           tmem_ld8_async(tacc + static_cast<uint32_t>((c8 + 2) * 8), va);
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
           tc_fence_before();                               // the whole accumulator sits in registers: hand it back
           mbar_arrive(&sm.acc_free[g][ab]);
         }
-        DGCN_T4_FILTER8(vb, 0, rbits + 8u);
+        DGCN_T4_FILTER8(vb, rbits + 8u);
       }
     }
 #undef DGCN_T4_FILTER8
@@ -399,36 +403,53 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
       const float lo = vK1 - 9.765625e-4f * (vK1 + sqq) - 2.0f * eps;
       bool ok = vK < INFINITY && (cut == INFINITY || hi < cut);
       int* selrow = sel + r * sel_ld;
+      uint32_t* bandj = reinterpret_cast<uint32_t*>(band + MB * TILE);   // [MB][TILE] candidate indices of the band
       int n_in = 0, nb = 0;
 #pragma unroll
       for (int u = 0; u < KP; ++u) {
         const float v = lk[u] == 0xFFFFFFFFu ? INFINITY : __uint_as_float(lk[u] & 0xFFFFF000u);
         const uint32_t j = lk[u] & 0xFFFu;
         const bool in = v < lo;                                        // the list ascends: a prefix
-        const bool bnd = ok && !in && v <= hi;
         if (in && u < K) {
           selrow[u] = static_cast<int>(j);
           n_in = u + 1;
         }
-        if (__any_sync(0xffffffffu, bnd)) {
-          const uint32_t jj = bnd ? j : static_cast<uint32_t>(qg);     // idle lanes read their own row
-          float dot = 0.f;
-#pragma unroll 2
-          for (int c = 0; c < C; c += 8) {
-            float q8[8], w[8];
-            ldg256(xqp + c, q8);
-            ldg256(xtb + jj * static_cast<uint32_t>(C) + c, w);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dot = fmaf(q8[i], w[i], dot);
-          }
-          if (bnd) {
-            const float d = (sqq + (-2.0f * dot)) + __ldg(sqb + j);
-            if (nb < MB) band[nb * TILE + r] = make_key(d, j);
-            ++nb;
-          }
+        if (ok && !in && v <= hi) {
+          if (nb < MB) bandj[nb * TILE + r] = j;
+          ++nb;
         }
       }
       if (nb > MB) ok = false;                                         // a cluster of near ties: exact completion kernel
+      // exact keys of the band, four independent FMA chains at a time; per candidate the chain is
+      // acc = fma(x_q[c], x_j[c], acc) for c ascending from acc = 0 - the bits of the fp32 kernel
+      const int nbe = ok ? nb : 0;
+      int nb_max = nbe;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nb_max = max(nb_max, __shfl_xor_sync(0xffffffffu, nb_max, o));
+      for (int m0 = 0; m0 < nb_max; m0 += 4) {
+        uint32_t jj[4];
+        float dot[4];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          jj[i4] = m0 + i4 < nbe ? bandj[(m0 + i4) * TILE + r] : static_cast<uint32_t>(qg);   // idle chains read the own row
+          dot[i4] = 0.f;
+        }
+#pragma unroll 1
+        for (int c = 0; c < C; c += 8) {
+          float q8[8];
+          ldg256(xqp + c, q8);
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            float w[8];
+            ldg256(xtb + jj[i4] * static_cast<uint32_t>(C) + c, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dot[i4] = fmaf(q8[i], w[i], dot[i4]);
+          }
+        }
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4)
+          if (m0 + i4 < nbe) band[(m0 + i4) * TILE + r] = make_key((sqq + (-2.0f * dot[i4])) + __ldg(sqb + jj[i4]), jj[i4]);
+      }
       if (ok) {
         const int need = K - n_in;                                     // 0 <= need <= nb
         int pos = n_in;
