@@ -296,7 +296,8 @@ __host__ __device__ __forceinline__ bool epilogue_wide_ok(const KnnArgs& a) {
   return (nch == 32 || nch == 64 || nch == 128) && (a.N & 7) == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0;
 }
 
-template <int NW, bool TRAIN, bool SEL_READY = false>
+// LB: neighbour rows a lane keeps in flight (one round trip to L2 per LB neighbours)
+template <int NW, bool TRAIN, bool SEL_READY = false, int LB = 10>
 __device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q0, const uint64_t* list,
                                                   const unsigned char* ok, int* sel, int sel_ld, float* red,
                                                   int cta, int tid) {
@@ -362,10 +363,10 @@ __device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q
       if (live) {
         p = __ldg(reinterpret_cast<const float4*>(self + static_cast<int64_t>(qg) * ld));
         const int* srow = sel + ql * sel_ld;
-        for (int l0 = 0; l0 < k; l0 += 10) {
-          float4 v[10];
+        for (int l0 = 0; l0 < k; l0 += LB) {
+          float4 v[LB];
 #pragma unroll
-          for (int u = 0; u < 10; ++u) {
+          for (int u = 0; u < LB; ++u) {
             const int idx = srow[min(l0 + u, k - 1)];
             v[u] = __ldg(reinterpret_cast<const float4*>(rows + static_cast<int64_t>(idx) * ld));
           }
@@ -373,7 +374,7 @@ __device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q
             // act is non-decreasing (slope >= 0) and so is the rounded p + q: max / min commute with them,
             // bit for bit - one FMNMX per gathered element (tail duplicates are harmless)
 #pragma unroll
-            for (int u = 0; u < 10; ++u) {
+            for (int u = 0; u < LB; ++u) {
               const float w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
@@ -383,7 +384,7 @@ __device__ __forceinline__ void cta_epilogue_wide(const KnnArgs& a, int b, int q
             }
           } else {
 #pragma unroll
-            for (int u = 0; u < 10; ++u) {
+            for (int u = 0; u < LB; ++u) {
               if (l0 + u < k) {
                 const float w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
                 const float pp[4] = {p.x, p.y, p.z, p.w};

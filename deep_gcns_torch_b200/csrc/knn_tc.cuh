@@ -286,7 +286,7 @@ struct ProloguePq {
   int M;
 };
 #ifndef DGCN_TEMPLATES_ONLY
-__global__ void __launch_bounds__(256) tc_prologue_pq_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C,
+__global__ void __launch_bounds__(256, 4) tc_prologue_pq_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int C,
                                                             int Cpad, int N, float* __restrict__ sq,
                                                             __nv_bfloat16* __restrict__ planes, float* __restrict__ xt,
                                                             float* __restrict__ sqmax, __nv_bfloat16* __restrict__ sqp,

@@ -431,17 +431,19 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
         float dot[4];
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
-          jj[i4] = m0 + i4 < nbe ? bandj[(m0 + i4) * TILE + r] : static_cast<uint32_t>(qg);   // idle chains read the own row
+          jj[i4] = m0 + i4 < nbe ? bandj[(m0 + i4) * TILE + r] : static_cast<uint32_t>(qg);
           dot[i4] = 0.f;
         }
+        // idle chains issue no loads: every lane-load is its own 32-byte sector request, and the request rate of
+        // such divergent loads - not bytes, not latency - is what bounds this phase
 #pragma unroll 1
         for (int c = 0; c < C; c += 8) {
-          float q8[8];
-          ldg256(xqp + c, q8);
+          float q8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (m0 < nbe) ldg256(xqp + c, q8);
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
-            float w[8];
-            ldg256(xtb + jj[i4] * static_cast<uint32_t>(C) + c, w);
+            float w[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (m0 + i4 < nbe) ldg256(xtb + jj[i4] * static_cast<uint32_t>(C) + c, w);
 #pragma unroll
             for (int i = 0; i < 8; ++i) dot[i4] = fmaf(q8[i], w[i], dot[i4]);
           }
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
         t.fail_list[slot] = b * N + qg;
       }
       t4_group_sync(g);
-      cta_epilogue_wide<4, false, true>(a, b, q0, nullptr, sm.ok[g], sel, sel_ld, nullptr, 0, r);
+      cta_epilogue_wide<4, false, true, 10>(a, b, q0, nullptr, sm.ok[g], sel, sel_ld, nullptr, 0, r);
     } else {
     // ---- exact re-rank of the listed candidates (fp32 FMA chain, channels ascending) --------------------------
     uint64_t* list = reinterpret_cast<uint64_t*>(qbase + g * T4_QBYTES);   // [KP][TILE]
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
     }
     t4_group_sync(g);
     // ---- consumer: sel lives in the group's candidate buffer ---------------------------------------------------
-    cta_epilogue_wide<4, false>(a, b, q0, list, sm.ok[g], sel, sel_ld, nullptr, 0, r);
+    cta_epilogue_wide<4, false, false, 10>(a, b, q0, list, sm.ok[g], sel, sel_ld, nullptr, 0, r);
     }
     }
   }
