@@ -37,7 +37,8 @@ def main():
     if "--regions" in sys.argv:
         src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
         open("/tmp/_src.csv", "w").write(src)
-        reg = subprocess.run([sys.executable, "tools/ncu_regions.py", "/tmp/_src.csv"], capture_output=True, text=True).stdout
+        tool = "tools/ncu_regions_tc4.py" if "knn_tc4_kernel" in out["kernel"] else "tools/ncu_regions.py"
+        reg = subprocess.run([sys.executable, tool, "/tmp/_src.csv"], capture_output=True, text=True).stdout
         out["regions_by_sass_landmarks"] = [l for l in reg.splitlines() if l.strip()]
     print(json.dumps(out, indent=1))
 
