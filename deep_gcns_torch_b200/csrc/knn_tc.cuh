@@ -78,6 +78,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spin > (1u << 26)) __trap();
   }
 }
+// the same wait with a suspend-time hint (ns): a warp that expects to wait long sleeps in the barrier unit instead of
+// spending issue slots on the retry loop
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -341,22 +359,24 @@ __global__ void __launch_bounds__(256, 4) tc_prologue_pq_kernel(const float* __r
   // 128-wide pass
   const int tx = tid & 15, ty = tid >> 4;
   for (int m0 = 0; m0 < M; m0 += 128) {
-    float acc[4][8];
+    // two outputs per instruction (fma.rn.f32x2: each half is the IEEE fma of the scalar code, so the chain per
+    // output - c ascending from 0 - and its bits are those of node_pq_kernel); the kernel is issue bound, not FMA-pipe bound
+    float2 acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
 #pragma unroll 4
     for (int c = 0; c < C; ++c) {
       const float4 a = *reinterpret_cast<const float4*>(xs + c * XLD + ty * 4);
       const float4 w0 = *reinterpret_cast<const float4*>(ws + c * M + m0 + tx * 4);
       const float4 w1 = *reinterpret_cast<const float4*>(ws + c * M + m0 + 64 + tx * 4);
       const float av[4] = {a.x, a.y, a.z, a.w};
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(make_float2(av[i], av[i]), wv[j], acc[i][j]);
     }
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bk + m0 + tx * 4));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bk + m0 + 64 + tx * 4));
@@ -364,9 +384,9 @@ __global__ void __launch_bounds__(256, 4) tc_prologue_pq_kernel(const float* __r
     for (int i = 0; i < 4; ++i) {
       float* row = g.pq + (static_cast<int64_t>(b) * N + n0 + ty * 4 + i) * M + m0;
       *reinterpret_cast<float4*>(row + tx * 4) =
-          make_float4(acc[i][0] + b0.x, acc[i][1] + b0.y, acc[i][2] + b0.z, acc[i][3] + b0.w);
+          make_float4(acc[i][0].x + b0.x, acc[i][0].y + b0.y, acc[i][1].x + b0.z, acc[i][1].y + b0.w);
       *reinterpret_cast<float4*>(row + 64 + tx * 4) =
-          make_float4(acc[i][4] + b1.x, acc[i][5] + b1.y, acc[i][6] + b1.z, acc[i][7] + b1.w);
+          make_float4(acc[i][2].x + b1.x, acc[i][2].y + b1.y, acc[i][3].x + b1.z, acc[i][3].y + b1.w);
     }
   }
 }

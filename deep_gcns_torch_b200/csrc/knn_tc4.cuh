@@ -210,12 +210,12 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
       for (int h = 0; h < H; ++h) {
         const int s = h & 1;
         if (pw == 0 && h + 1 < H) {                        // refill the other stage: its MMAs (half-tile h-1) must be done
-          if (h >= 1) mbar_wait(&sm.stage_free[s ^ 1], static_cast<uint32_t>(((h - 1) >> 1) & 1));
+          if (h >= 1) mbar_wait_hint(&sm.stage_free[s ^ 1], static_cast<uint32_t>(((h - 1) >> 1) & 1), 1000u);
           if (leader) tma_tile(h + 1);
           __syncwarp();
         }
-        mbar_wait(&sm.full[s], static_cast<uint32_t>((h >> 1) & 1));
-        if (h >= 2) mbar_wait(&sm.acc_free[g][s], static_cast<uint32_t>(((h >> 1) - 1) & 1));
+        mbar_wait_hint(&sm.full[s], static_cast<uint32_t>((h >> 1) & 1), 1000u);
+        if (h >= 2) mbar_wait_hint(&sm.acc_free[g][s], static_cast<uint32_t>(((h >> 1) - 1) & 1), 1000u);
         tc_fence_after();
         const uint32_t bbase = smem_u32(stage0 + s * T4_STAGE_BYTES);
         const uint64_t dsx = umma_desc_mn_sw128(smem_u32(sx0 + s * T4_SX_BYTES), 2048, 1024);
