@@ -318,7 +318,18 @@ __global__ void __launch_bounds__(256, 4) tc_prologue_pq_kernel(const float* __r
   const int M = g.M;
   const int64_t plane = static_cast<int64_t>(Cpad) * N;
   __nv_bfloat16* pb = planes + static_cast<int64_t>(b) * TC_PLANES * plane;
-  {
+  if (((reinterpret_cast<uintptr_t>(x) & 7) | (sb & 1) | (sc & 1)) == 0) {
+    // two adjacent points per thread: 8-byte loads, one bf16x2 store per plane (each half rounded like the scalar path)
+    const int lane = tid & 31, wrp = tid >> 5, n = n0 + 2 * lane;
+    for (int c = wrp; c < Cpad; c += 8) {
+      const float2 v = c < C ? __ldg(reinterpret_cast<const float2*>(x + b * sb + c * sc + n)) : make_float2(0.f, 0.f);
+      if (c < C) *reinterpret_cast<float2*>(xs + c * XLD + 2 * lane) = v;
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(v.x, v.y);
+      const __nv_bfloat162 mid = __floats2bfloat162_rn(v.x - __low2float(hi), v.y - __high2float(hi));
+      *reinterpret_cast<__nv_bfloat162*>(pb + static_cast<int64_t>(c) * N + n) = hi;
+      *reinterpret_cast<__nv_bfloat162*>(pb + plane + static_cast<int64_t>(c) * N + n) = mid;
+    }
+  } else {
     const int tx = tid & 63, ty = tid >> 6, n = n0 + tx;
     for (int c = ty; c < Cpad; c += 4) {
       const float v = c < C ? __ldg(x + b * sb + c * sc + n) : 0.f;
@@ -349,7 +360,16 @@ __global__ void __launch_bounds__(256, 4) tc_prologue_pq_kernel(const float* __r
     const float m = warp_max(s);
     if ((tid & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(sqmax + b), __float_as_uint(m));
   }
-  if (xt) {
+  if (xt && (C & 7) == 0 && (reinterpret_cast<uintptr_t>(xt) & 15) == 0) {
+    // node-major copy: a warp step covers 16 points x 8 channels - lane pairs write one full 32-byte sector of a row,
+    // and the transposed shared-memory reads ((c0 + 4 (lane & 1) + j) * 68 + lane / 2) hit 32 distinct banks
+    const int lane = tid & 31, wrp = tid >> 5;
+    for (int it = wrp; it < 4 * (C >> 3); it += 8) {
+      const int rr = (lane >> 1) + 16 * (it & 3), c = (it >> 2) * 8 + 4 * (lane & 1);
+      const float4 v = make_float4(xs[c * XLD + rr], xs[(c + 1) * XLD + rr], xs[(c + 2) * XLD + rr], xs[(c + 3) * XLD + rr]);
+      *reinterpret_cast<float4*>(xt + (static_cast<int64_t>(b) * N + n0 + rr) * C + c) = v;
+    }
+  } else if (xt) {
     for (int i = tid; i < 64 * C; i += 256) {
       const int rr = i / C, c = i - rr * C;
       xt[(static_cast<int64_t>(b) * N + n0 + rr) * C + c] = xs[c * XLD + rr];
