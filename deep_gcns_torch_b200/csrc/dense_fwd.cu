@@ -49,7 +49,7 @@ size_t knn_workspace_bytes(int64_t B, int64_t C, int64_t N, int64_t K) {
     const int64_t ldd = (N + 3) / 4 * 4;
     const size_t nslab = static_cast<size_t>(B) > knn_slab_clouds(B, N) ? 2 : 1;   // two slabs: distance rows of slab s+1 overlap the select of slab s
     bytes += nslab * align_up(knn_slab_clouds(B, N) * N * ldd * 4, 256);
-    bytes += align_up(knn_slab_clouds(B, N) * N * 4 + 256, 256);   // rows the sampled select hands to the exact kernel
+    bytes += nslab * align_up(knn_slab_clouds(B, N) * N * 4 + 256, 256);   // rows the sampled select hands to the exact kernel (one list per slab buffer)
     if (C <= TC_MAX_C && N >= TILE && N % TILE == 0) bytes += align_up(dist_rows_tc_plane_elems(B, C, N) * 2, 256);   // (hi, mid, lo) planes
   }
   return bytes + 256;
@@ -270,28 +270,31 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
   if (warps_f < 1) warps_f = 1;
   const size_t smem_f = per_warp_f * warps_f;
   int* rowlist = nullptr;
+  int* rowlist2 = nullptr;
   if (fast) {
     rowlist = ws.take<int>(static_cast<size_t>(nbmax) * N + 64);
+    if (drows2) rowlist2 = ws.take<int>(static_cast<size_t>(nbmax) * N + 64);
     if (!ws.ok) return DGCN_ERR_WORKSPACE;
     DGCN_ENSURE_SMEM((select_rows_fast_kernel), smem_f);
   }
   KernelTimer timer(stream, "knn");
-  // Two-stream slab pipeline: the FMA-bound distance rows of slab s+1 (side stream) run under the latency-bound
-  // per-row select of slab s (caller's stream); events fork the side stream from the caller's stream and join it
-  // back, so the call is still one stream-ordered operation for the caller (and capturable in a CUDA graph).
+  // Two-chain slab pipeline: even slabs run (distance rows -> sampled select -> exact completion) on the caller's
+  // stream, odd slabs on a side stream with their own row buffer and completion list.  The chains overlap freely:
+  // the tensor-core distance rows of one slab run under the instruction-bound select of the other, and - what pays
+  // most - the partial last wave of one select (4096 rows are 1.15 .. 2.3 waves of its CTAs) is filled by the CTAs
+  // of the other chain.  An event forks the side stream from the caller's stream and one joins it back, so the call
+  // is still one stream-ordered operation for the caller (and capturable in a CUDA graph).
   cudaStream_t side = drows2 ? slab_side_stream() : nullptr;
-  cudaEvent_t ev_dist[2] = {nullptr, nullptr}, ev_sel[2] = {nullptr, nullptr}, ev_start = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_join = nullptr;
   if (side) {
-    bool okev = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 2 && okev; ++i)
-      okev = cudaEventCreateWithFlags(&ev_dist[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ev_sel[i], cudaEventDisableTiming) == cudaSuccess;
-    if (!okev) side = nullptr;
+    if (cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
+      side = nullptr;
   }
   struct EventGuard {   // destroying an event that is still in flight is legal: it is released on completion
-    cudaEvent_t* e[5];
+    cudaEvent_t* e[2];
     ~EventGuard() { for (cudaEvent_t* p : e) if (p && *p) cudaEventDestroy(*p); }
-  } guard{{&ev_start, &ev_dist[0], &ev_dist[1], &ev_sel[0], &ev_sel[1]}};
+  } guard{{&ev_start, &ev_join}};
   if (side) {
     DGCN_CUDA_TRY(cudaEventRecord(ev_start, stream));
     DGCN_CUDA_TRY(cudaStreamWaitEvent(side, ev_start, 0));
@@ -300,39 +303,33 @@ int launch_knn(KnnArgs& a, Workspace& ws, cudaStream_t stream, int64_t* n_partia
   for (int b0 = 0; b0 < B; b0 += nbmax, ++slab) {
     const int nb = (B - b0 < nbmax) ? (B - b0) : nbmax;
     const int buf = side ? (slab & 1) : 0;
+    cudaStream_t st = buf ? side : stream;             // a buffer is only ever touched by its own chain: stream order
     float* drows_s = buf ? drows2 : drows;
-    if (side) {
-      if (slab >= 2) DGCN_CUDA_TRY(cudaStreamWaitEvent(side, ev_sel[buf], 0));   // the select two slabs back has left this buffer
-      if (rows_on_tc) {
-        int rc = dist_rows_tc_launch(a, planes3, b0, nb, drows_s, ldd, side);
-        if (rc != DGCN_OK) return rc;
-      } else {
-        dist_rows_kernel<<<dim3(ceil_div(N, TILE), ceil_div(N, TILE), nb), NTHREADS, 0, side>>>(a, b0, drows_s, ldd);
-        DGCN_LAUNCH_CHECK();
-      }
-      DGCN_CUDA_TRY(cudaEventRecord(ev_dist[buf], side));
-      DGCN_CUDA_TRY(cudaStreamWaitEvent(stream, ev_dist[buf], 0));
-    } else if (rows_on_tc) {
-      int rc = dist_rows_tc_launch(a, planes3, b0, nb, drows_s, ldd, stream);
+    int* rowlist_s = buf ? rowlist2 : rowlist;
+    if (rows_on_tc) {
+      int rc = dist_rows_tc_launch(a, planes3, b0, nb, drows_s, ldd, st);
       if (rc != DGCN_OK) return rc;
     } else {
-      dist_rows_kernel<<<dim3(ceil_div(N, TILE), ceil_div(N, TILE), nb), NTHREADS, 0, stream>>>(a, b0, drows_s, ldd);
+      dist_rows_kernel<<<dim3(ceil_div(N, TILE), ceil_div(N, TILE), nb), NTHREADS, 0, st>>>(a, b0, drows_s, ldd);
       DGCN_LAUNCH_CHECK();
     }
     const int64_t rows = static_cast<int64_t>(nb) * N;
     if (fast) {
-      DGCN_CUDA_TRY(cudaMemsetAsync(rowlist, 0, 256, stream));
-      select_rows_fast_kernel<<<static_cast<unsigned>(ceil_div(rows, warps_f)), warps_f * 32, smem_f, stream>>>(
-          a, b0, nb, drows_s, ldd, cap, sample_rank, warps_f, rowlist, rowlist + 64);
+      DGCN_CUDA_TRY(cudaMemsetAsync(rowlist_s, 0, 256, st));
+      select_rows_fast_kernel<<<static_cast<unsigned>(ceil_div(rows, warps_f)), warps_f * 32, smem_f, st>>>(
+          a, b0, nb, drows_s, ldd, cap, sample_rank, warps_f, rowlist_s, rowlist_s + 64);
       DGCN_LAUNCH_CHECK();
-      select_rows_kernel<<<296, warps * 32, smem, stream>>>(a, b0, nb, drows_s, ldd, KP, ldd, warps, rowlist + 64, rowlist);
+      select_rows_kernel<<<296, warps * 32, smem, st>>>(a, b0, nb, drows_s, ldd, KP, ldd, warps, rowlist_s + 64, rowlist_s);
       DGCN_LAUNCH_CHECK();
     } else {
-      select_rows_kernel<<<static_cast<unsigned>(ceil_div(rows, warps)), warps * 32, smem, stream>>>(
+      select_rows_kernel<<<static_cast<unsigned>(ceil_div(rows, warps)), warps * 32, smem, st>>>(
           a, b0, nb, drows_s, ldd, KP, ldd, warps, nullptr, nullptr);
       DGCN_LAUNCH_CHECK();
     }
-    if (side) DGCN_CUDA_TRY(cudaEventRecord(ev_sel[buf], stream));
+  }
+  if (side) {
+    DGCN_CUDA_TRY(cudaEventRecord(ev_join, side));
+    DGCN_CUDA_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
   }
   return DGCN_OK;
 }
