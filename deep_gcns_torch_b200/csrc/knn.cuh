@@ -848,26 +848,50 @@ __global__ void select_rows_fast_kernel(const KnnArgs a, int b0, int nb, const f
   if (row >= static_cast<int64_t>(nb) * N) return;   // whole warp exits together
   const int b = b0 + static_cast<int>(row / N), q = static_cast<int>(row % N);
   const float* drow = drows + row * ldd;
-  // 1. sample 128 keys spread over the row, sort them, take the sample_rank-th as the bound
+  // 1. sample 128 keys spread over the row, sort them, take the sample_rank-th as the bound.  The sort runs in
+  //    registers: element e = 32 u + lane lives in smp[u] of lane `lane`; exchange distances below 32 are warp
+  //    shuffles, 32 and 64 are register pairs (a shared-memory bitonic sort of these 128 keys was a third of this
+  //    kernel's time, all of it shared-memory latency between dependent stages).
+  uint32_t smp[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int s = lane + 32 * u;
     const int i = static_cast<int>((static_cast<int64_t>(s) * N) >> 7);
     uint32_t key = float_to_ordered(__ldg(drow + i));
     if (a.exclude_self && i == q) key = 0xFFFFFFFFu;
-    sk[s] = static_cast<uint64_t>(key);
+    smp[u] = key;
   }
   // the first 128 distances of the row: in flight under the sample sort
   float first[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) first[u] = (u * 32 + lane < N) ? __ldg(drow + u * 32 + lane) : 0.f;
-  __syncwarp();
-  warp_bitonic_sort(sk, 128, lane);
-  // keep the sorted sample in registers: lane l holds samples l, l+32, l+64, l+96
-  uint32_t smp[4];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) smp[u] = static_cast<uint32_t>(sk[lane + 32 * u]);
-  __syncwarp();
+  for (int kk = 2; kk <= 128; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j < 32) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, smp[u], j);
+          const bool up = (((32 * u + lane) & kk) == 0);      // ascending block
+          const bool lower = (lane & j) == 0;                   // this element is the lower index of its pair
+          smp[u] = (lower == up) ? min(smp[u], other) : max(smp[u], other);
+        }
+      } else {
+        const int jr = j >> 5;                                  // partner register: u ^ jr, same lane
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if ((u & jr) == 0) {
+            const bool up = (((32 * u) & kk) == 0);
+            const uint32_t lo = min(smp[u], smp[u ^ jr]), hi = max(smp[u], smp[u ^ jr]);
+            smp[u] = up ? lo : hi;
+            smp[u ^ jr] = up ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+  // lane l now holds the sorted samples l, l+32, l+64, l+96
   // 2. compaction in index order of every distance <= bound; if the sample misjudged the row (too few or too
   //    many below the bound) move the bound along the sorted sample and try again.  The pass is the bulk of
   //    this kernel's instructions, so it works on the raw floats: one FSETP against the bound (a float compare
