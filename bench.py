@@ -126,7 +126,7 @@ class ClockSampler:
 
     The timed region of the default run lasts ~10 ms, far below nvidia-smi's 100-200 ms loop period, so the
     samples come from NVML directly (the library nvidia-smi itself reads: `clocks.sm`, `clocks.max.sm`,
-    `clocks_event_reasons.*`), polled from a thread every ~0.5 ms between __enter__ and __exit__; the
+    `clocks_event_reasons.*`), polled from a thread every ~2 ms between __enter__ and __exit__; the
     nvidia-smi loop of the profiling recipe is the fallback when pynvml is unavailable."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -172,7 +172,7 @@ class ClockSampler:
                 self._poll_once()
             except Exception:
                 return
-            time.sleep(0.0005)
+            time.sleep(0.002)      # a poll holds the GIL for tens of microseconds: keep it rare next to a 0.26 ms step
 
     def __enter__(self):
         self.stop.clear()
@@ -362,9 +362,19 @@ def sparse_aggregate_block(dev, steps=10):
     return res
 
 
+def _claim_stdout():
+    """Keep stdout to the ONE JSON line: file descriptor 1 is pointed at stderr for the whole run (NCCL prints its
+    version banner to fd 1 from C, torch prints warnings), the JSON line is written to a saved copy of the real stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
+    json_out = _claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -400,6 +410,11 @@ def run_native(args):
         beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clocks:
             barrier()
+            # ~2 ms spin kernel ahead of the first event: the host enqueues the first steps behind it, so the K timed
+            # steps run back to back as they do in steady state (a step is ~0.25 ms of GPU time against ~0.2 ms of
+            # host-side launch work: without the head start the first-launch latency after the synchronize is 5-15 %
+            # of a 20-step region; the `sustained` block below is the same loop over ~2 s without any of this)
+            torch.cuda._sleep(4_000_000)
             beg.record()
             for i in range(args.steps):
                 mod(xs[i % N_ROTATE])
@@ -513,6 +528,8 @@ def run_native(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "edges_per_step_per_gpu": EDGES_PER_STEP, "parallelism": "batch-sharded x%d" % world,
                    "l2": "inputs rotate over %d distinct 16.8 MB batches (134 MB > 126 MB L2)" % N_ROTATE,
+                   "queue": "the K timed steps are enqueued behind a ~2 ms spin kernel (device-side throughput; CUDA events "
+                            "bracket exactly the K steps)",
                    "host_binding": numa},
         "e2e": {"value": EDGES_PER_STEP * world * args.steps / (ms_e2e * 1e-3), "unit": "edges/s",
                 "h2d_bytes_per_step": B * C * N * 4, "d2h_bytes_per_step": B * C * N * 4,
@@ -562,7 +579,8 @@ def run_native(args):
                                          "%d threads = fastest of %s (%d hardware threads available)"
                                          % (xc.shape[0], B, reps, dt, threads, thread_candidates(),
                                             len(os.sched_getaffinity(0)))}
-    print(json.dumps(out))
+    json_out.write(json.dumps(out) + "\n")
+    json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
