@@ -2,26 +2,35 @@
 //
 //   Why: knn_tc_kernel is bound by per-warp instruction latency at 8 warps per SM (255 registers, two CTAs whose
 //   TMEM accumulators fill the 512 columns) and 512 query tiles on 296 CTA slots are 1.73 waves.  Here a CTA is
-//   four warpgroups (16 filter warps, <= 120 registers each) + one producer warp; the four warpgroups own four
-//   128-query tiles of the SAME cloud, so a candidate tile is brought in once (TMA) and multiplied against four
-//   resident query operands; B*N/512 CTAs are a single wave on the 148 SMs for the headline shape.
+//   four filter warpgroups (16 warps) + four producer warps; the four warpgroups own four 128-query tiles of the
+//   SAME cloud, so a candidate tile is brought in once (TMA) and multiplied against four resident query operands;
+//   B*N/512 CTAs are a single wave on the 148 SMs for the headline shape.  Registers: launched at 640 x 96,
+//   setmaxnreg moves the producers' share to the filters (512 x 112 + 128 x 32 = the same 61,440).
 //
-//   producer warp (lane 0)   TMA: query planes of the four tiles once, then 64-candidate half-tiles into a
-//                            two-stage ring (stage of half-tile h+1 is refilled as soon as the MMAs of h-1 have
-//                            completed - tcgen05.commit on stage_free);  MMA: per half-tile and group
-//                            3*Cpad/16 + 1 tcgen05.mma (M=128, N=64, K=16) into one of the group's two 64-column
-//                            TMEM accumulators, issued to whichever group has drained that accumulator first
-//                            (non-blocking mbarrier tests), commit -> acc_full[g][h&1].
-//   filter warpgroup g       thread r = TMEM lane r = query r of tile g: wait acc_full, tcgen05.ld 16 columns
-//                            ahead, threshold test -> private candidate buffer (shared memory, slot-major);
-//                            the accumulator is handed back (acc_free) as soon as its last chunk sits in
-//                            registers.  FLUSH = sorting network instead of one insertion per entry: the batch
-//                            (<= 16 entries per lane) is bitonic-sorted in registers, min-merged against the upper
-//                            half of the 32-entry sorted register list and the list re-sorted by one 32-input
-//                            bitonic merge - a fixed ~450 instructions per warp-wide flush whatever the lanes'
-//                            counts (the insertion loop costs ~80 per ROUND, rounds = the fullest lane's count).
-//                            Then: exact fp32 re-rank, certificate, fused consumer - as in knn_tc_kernel, per
-//                            warpgroup (named barriers), in the group's own (now idle) query-plane memory.
+//   producer warp pw         issues the MMAs of warpgroup pw: per half-tile 3*Cpad/16 + 1 tcgen05.mma (M=128, N=64,
+//                            K=16) into one of the group's two 64-column TMEM accumulators (4 x 2 x 64 = all 512
+//                            columns) once the stage has landed (full[s]) and the group has drained that
+//                            accumulator (acc_free[g]); commit -> acc_full[g][h&1] and one arrival on stage_free[s].
+//                            Warp-uniform control flow, one elected lane issues: the descriptors stay in uniform
+//                            registers.  Producer warp 0 also moves the operands by TMA: the query planes of the
+//                            four tiles once, then 64-candidate half-tiles into a two-stage ring (the stage of
+//                            half-tile h+1 is refilled as soon as every group's MMAs of h-1 have completed).
+//   filter warpgroup g       thread r = TMEM lane r = query r of tile g: wait acc_full, tcgen05.ld 8 columns ahead,
+//                            threshold test -> private candidate buffer (shared memory, slot-major); the
+//                            accumulator is handed back (acc_free) as soon as its last chunk sits in registers.
+//                            FLUSH = sorting network instead of one insertion per entry: the batch (<= 16 entries
+//                            per lane, a second pass for slots 16..23) is bitonic-sorted in registers, min-merged
+//                            against the upper half of the 32-entry sorted register list and the list re-sorted by
+//                            one 32-input bitonic merge - a fixed ~450 instructions per warp-wide flush whatever
+//                            the lanes' counts (the insertion loop costs ~80 per ROUND, rounds = the fullest
+//                            lane's count).
+//                            Then, per warpgroup (named barriers) in the group's own (now idle) query-plane memory:
+//                            - set-only consumers (every rank kept, no index output, no self exclusion): membership
+//                              by interval arithmetic on the approximate list, exact fp32 chains only inside the
+//                              ambiguous band around rank K;
+//                            - otherwise the exact fp32 re-rank of all listed candidates and the certificate of
+//                              knn_tc_kernel;
+//                            and the fused consumer (cta_epilogue_wide).
 //
 // Eligibility (host side, launch_knn_tc): packed entries (N <= 4096), K <= 20 (list of 28 or 16), C % 8 == 0,
 // 32-byte aligned node-major copy, wide consumer, no train-mode statistics.  Everything else keeps knn_tc_kernel.
