@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) knn_tc4_kernel(const __grid_con
   unsigned char* cbuf0 = qx + TC_XBLOCK_BYTES;                              // [group][slot][128 threads] u32
   T4Tail& sm = *reinterpret_cast<T4Tail*>(cbuf0 + T4_GROUPS * T4_CBUF_BYTES);
   const KnnArgs& a = t.a;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.y;
   const int N = a.N, Cpad = t.Cpad;
   const int qt0 = blockIdx.x * T4_GROUPS;                                   // first query tile of this CTA
