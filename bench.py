@@ -7,7 +7,11 @@ B=16 N=4096 k=20 C=64 - BASELINE.json's metric shape) on N B200s.
 One "step" = one pass of the hot path over one batch of 16 synthetic clouds
 (1,310,720 edges).  Multi-GPU: the batch dimension is sharded, every rank owns its
 own 16 clouds (weak scaling, no data-path collective - clouds are independent,
-SURVEY.md 8e).  Prints ONE JSON line (rank 0).
+SURVEY.md 8e).  Prints ONE JSON line (rank 0; file descriptor 1 is pointed at stderr
+for everything else - NCCL's version banner, warnings).  The K timed steps are
+enqueued behind a ~2 ms spin kernel and bracketed by CUDA events: a step is ~0.25 ms
+of GPU time, so the host's first-launch latency after the synchronize would otherwise
+be several percent of a 20-step region.
 
 `--impl reference` times the reference's CPU algorithm (the oracle port: the
 reference is pure Python/torch, there is nothing to compile into oracle/_ref) on the
