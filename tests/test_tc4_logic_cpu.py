@@ -133,3 +133,36 @@ def test_interval_membership_equals_exact_top_k():
         want = {u for u in range(KP) if exact_key[u] in set(all_keys)}
         assert got == want and len(got) == K, trial
     assert answered > 2000
+
+
+def _f2u(x):
+    return np.asarray(x, dtype=np.float32).view(np.uint32)
+
+
+def _u2f(u):
+    return np.asarray(u, dtype=np.uint32).view(np.float32)
+
+
+def test_list_value_brackets_the_approximate_distance_within_delta():
+    """The interval test assumes a_c <= approx_c <= a_c + delta(a_c) with delta(v) = 2^-10 (v + |x_i|^2) for the value
+    a_c a list entry carries.  Restate the device path of a candidate - accumulator -> 20-bit packed buffer entry ->
+    upper bound of the accumulator -> d2 = max(fma(-2, ab, |x_i|^2), 0) -> 20-bit list value - in float32 and check the
+    bracket against the accumulator's own distance, over magnitudes from 1e-3 to 1e6 and both accumulator signs."""
+    rng = np.random.default_rng(2)
+    for scale in (1e-3, 1.0, 64.0, 1e3, 1e6):
+        sqq = np.float32(scale * rng.uniform(0.2, 2.0))
+        # approximate squared distances around and far above |x_i|^2 (accumulator negative and positive)
+        d2 = np.concatenate([rng.uniform(0, 4 * scale, 200000), rng.uniform(0, 1e-3 * scale, 2000),
+                             np.geomspace(1e-6 * scale, 64 * scale, 2000)])
+        acc = ((np.float64(sqq) - d2) * 0.5).astype(np.float32)         # the tensor core's accumulator = -key/2
+        approx = np.float64(sqq) - 2.0 * acc.astype(np.float64)          # the distance that accumulator stands for
+        idx = rng.integers(0, 4096, size=acc.size).astype(np.uint32)
+        en = (_f2u(acc) & np.uint32(0xFFFFF000)) | idx                    # filter: one LOP3
+        neg = (en & np.uint32(0x80000000)) != 0
+        ab = _u2f(np.where(neg, en & np.uint32(0xFFFFF000), en | np.uint32(0xFFF)))
+        d2p = np.maximum((np.float64(-2.0) * ab.astype(np.float64) + np.float64(sqq)).astype(np.float32), np.float32(0))
+        a = _u2f(_f2u(d2p) & np.uint32(0xFFFFF000)).astype(np.float64)   # the list value
+        slack = 2.0 ** -22 * (np.abs(approx) + float(sqq))               # one fp32 rounding of the fma, inside eps
+        assert np.all(a <= np.maximum(approx, 0) + slack)
+        delta = 2.0 ** -10 * (a + float(sqq))
+        assert np.all(np.maximum(approx, 0) <= a + delta + slack)
