@@ -166,3 +166,37 @@ def test_list_value_brackets_the_approximate_distance_within_delta():
         assert np.all(a <= np.maximum(approx, 0) + slack)
         delta = 2.0 ** -10 * (a + float(sqq))
         assert np.all(np.maximum(approx, 0) <= a + delta + slack)
+
+
+def test_shuffle_bitonic_sort_of_the_128_key_sample():
+    """select_rows_fast_kernel sorts its 128-key sample in registers: element e = 32 u + lane lives in smp[u] of
+    lane `lane`; exchange distances below 32 are __shfl_xor, 32 and 64 are register pairs.  A wrong network would
+    not break results (the sample only bounds the K-th distance) - it would silently cost retries - so the
+    direction logic is restated here and checked against a plain sort."""
+    rng = np.random.default_rng(3)
+    for trial in range(50):
+        keys = rng.integers(0, 2**32, size=128, dtype=np.uint64).astype(np.uint32)
+        if trial % 5 == 0:
+            keys[rng.integers(0, 128, size=40)] = keys[0]                 # duplicates
+        smp = keys.reshape(4, 32).copy()                                  # smp[u][lane]
+        lane = np.arange(32)
+        kk = 2
+        while kk <= 128:
+            j = kk >> 1
+            while j > 0:
+                if j < 32:
+                    for u in range(4):
+                        other = smp[u][lane ^ j]                          # __shfl_xor_sync(..., j)
+                        up = ((32 * u + lane) & kk) == 0
+                        lower = (lane & j) == 0
+                        smp[u] = np.where(lower == up, np.minimum(smp[u], other), np.maximum(smp[u], other))
+                else:
+                    jr = j >> 5
+                    for u in range(4):
+                        if (u & jr) == 0:
+                            up = ((32 * u) & kk) == 0
+                            lo, hi = np.minimum(smp[u], smp[u ^ jr]), np.maximum(smp[u], smp[u ^ jr])
+                            smp[u], smp[u ^ jr] = (lo, hi) if up else (hi, lo)
+                j >>= 1
+            kk <<= 1
+        assert np.array_equal(smp.reshape(-1), np.sort(keys))             # lane l holds samples l, l+32, l+64, l+96
